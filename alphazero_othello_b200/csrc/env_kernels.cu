@@ -1,0 +1,611 @@
+// Othello environment kernels for B200 (sm_100a) and their C ABI.
+// Reference behaviour: envs/othello.py (OthelloGameNew / _BitBoard); see
+// include/othello_b200.h for the per-entry citations.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/othello_b200.h"
+#include "bitboard.cuh"
+#include "common.cuh"
+#include "philox.cuh"
+
+using namespace oth;
+
+// ------------------------------------------------------------- kernels ----
+
+// Two positions per thread: 128-bit loads/stores of packed uint64 boards.
+__global__ void __launch_bounds__(256) k_legal_moves(const u64* __restrict__ own, const u64* __restrict__ opp,
+                                                     u64* __restrict__ out, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t npair = n >> 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += stride) {
+        const ulonglong2 a = reinterpret_cast<const ulonglong2*>(own)[i];
+        const ulonglong2 b = reinterpret_cast<const ulonglong2*>(opp)[i];
+        ulonglong2 m;
+        m.x = legal_moves(a.x, b.x);
+        m.y = legal_moves(a.y, b.y);
+        reinterpret_cast<ulonglong2*>(out)[i] = m;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = legal_moves(own[n - 1], opp[n - 1]);
+}
+
+__device__ __forceinline__ void step_one(u64 o, u64 p, int a, u64& no, u64& np, u64& nm, unsigned& fl)
+{
+    fl = 0;
+    u64 f = 0;
+    if (a != OTH_PASS) {
+        const u64 x = (a >= 0 && a < 64) ? (1ULL << a) : 0ULL;
+        f = (x & ~(o | p)) ? flips(o, p, x) : 0ULL;
+        if (f == 0) {  // envs/othello.py:419-421 -> ValueError
+            no = o;
+            np = p;
+            nm = legal_moves(o, p);
+            fl = OTH_F_ILLEGAL;
+            return;
+        }
+    }
+    const Board b = apply_move(o, p, a, f);
+    no = b.own;
+    np = b.opp;
+    nm = legal_moves(no, np);
+    int v;
+    const int st = position_status(no, np, nm, &v);
+    if (st == 1) fl |= OTH_F_MUST_PASS;
+    if (st == 2) {
+        // v is from the next mover's side; the mover who just played sees -v
+        fl |= OTH_F_TERMINAL;
+        if (v < 0) fl |= OTH_F_WIN;
+        if (v > 0) fl |= OTH_F_LOSS;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_step(const u64* __restrict__ own, const u64* __restrict__ opp,
+                                              const uint8_t* __restrict__ action, u64* __restrict__ out_own,
+                                              u64* __restrict__ out_opp, u64* __restrict__ out_moves,
+                                              uint8_t* __restrict__ out_flags, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u64 no, np, nm;
+        unsigned fl;
+        step_one(own[i], opp[i], action[i], no, np, nm, fl);
+        out_own[i] = no;
+        out_opp[i] = np;
+        if (out_moves) out_moves[i] = nm;
+        if (out_flags) out_flags[i] = (uint8_t)fl;
+    }
+}
+
+// One thread per game, whole game in registers.
+__global__ void __launch_bounds__(256) k_rollout(uint64_t seed, uint64_t base, int64_t n_games, int32_t* __restrict__ out_score,
+                                                 int32_t* __restrict__ out_plies, u64* __restrict__ out_final, int64_t n_trace,
+                                                 uint8_t* __restrict__ trace_actions, u64* __restrict__ trace_moves,
+                                                 unsigned long long* __restrict__ counters)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long my_plies = 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_games; g += stride) {
+        const uint64_t gid = base + (uint64_t)g;
+        const bool tr = g < n_trace;
+        u64 own = INIT_BLACK, opp = INIT_WHITE;
+        int side = 0;  // 0: +1 (black) to move
+        int plies = 0;
+        u64 m = legal_moves(own, opp);
+        Philox4 r = {0, 0, 0, 0};
+        while (plies < OTH_MAX_PLIES) {
+            if ((plies & 3) == 0) r = philox4x32_10(seed, gid, (uint32_t)(plies >> 2), 0u);
+            const int w = plies & 3;
+            const uint32_t rnd = w == 0 ? r.x : (w == 1 ? r.y : (w == 2 ? r.z : r.w));
+            const int nm = __popcll(m);
+            const int k = (int)__umulhi(rnd, (uint32_t)nm);
+            const int sq = nth_set_bit(m, k);
+            if (tr) {
+                if (trace_actions) trace_actions[g * OTH_MAX_PLIES + plies] = (uint8_t)sq;
+                if (trace_moves) trace_moves[g * OTH_MAX_PLIES + plies] = m;
+            }
+            const u64 f = flips(own, opp, 1ULL << sq);
+            const Board b = apply_move(own, opp, sq, f);
+            own = b.own;
+            opp = b.opp;
+            side ^= 1;
+            plies++;
+            m = legal_moves(own, opp);
+            if (m == 0) {
+                const u64 m2 = legal_moves(opp, own);
+                if (m2 == 0) break;  // neither side can move: terminal (envs/othello.py:440-454)
+                if (plies >= OTH_MAX_PLIES) break;
+                if (tr) {  // forced pass is a ply of its own (self_play_worker.py:88)
+                    if (trace_actions) trace_actions[g * OTH_MAX_PLIES + plies] = OTH_PASS;
+                    if (trace_moves) trace_moves[g * OTH_MAX_PLIES + plies] = 0;
+                }
+                const u64 t = own;
+                own = opp;
+                opp = t;
+                side ^= 1;
+                plies++;
+                m = m2;
+            }
+        }
+        if (tr && trace_actions)
+            for (int p = plies; p < OTH_MAX_PLIES; p++) trace_actions[g * OTH_MAX_PLIES + p] = 0xFF;
+        const u64 black = side == 0 ? own : opp, white = side == 0 ? opp : own;
+        if (out_score) out_score[g] = __popcll(black) - __popcll(white);
+        if (out_plies) out_plies[g] = plies;
+        if (out_final) {
+            out_final[2 * g] = black;
+            out_final[2 * g + 1] = white;
+        }
+        my_plies += plies;
+    }
+    if (counters) {
+        for (int o = 16; o; o >>= 1) my_plies += __shfl_xor_sync(0xffffffffu, my_plies, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(counters, my_plies);
+    }
+}
+
+// One warp per board: cells -> bitboards by ballot (envs/othello.py:358-371).
+__device__ __forceinline__ void warp_pack(const int8_t* __restrict__ s, int player, int lane, u64& own, u64& opp)
+{
+    const int c0 = s[lane], c1 = s[lane + 32];
+    const unsigned o_lo = __ballot_sync(0xffffffffu, c0 == player), o_hi = __ballot_sync(0xffffffffu, c1 == player);
+    const unsigned p_lo = __ballot_sync(0xffffffffu, c0 == -player), p_hi = __ballot_sync(0xffffffffu, c1 == -player);
+    own = ((u64)o_hi << 32) | o_lo;
+    opp = ((u64)p_hi << 32) | p_lo;
+}
+
+__global__ void __launch_bounds__(256) k_pack(const int8_t* __restrict__ states, const int8_t* __restrict__ players,
+                                              u64* __restrict__ own, u64* __restrict__ opp, int64_t n)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nw) {
+        u64 o, p;
+        warp_pack(states + i * 64, players ? players[i] : 1, lane, o, p);
+        if (lane == 0) {
+            own[i] = o;
+            opp[i] = p;
+        }
+    }
+}
+
+// bitboards -> int8 cells; own discs get the value `player` (envs/othello.py:374-388, 430-433).
+__global__ void __launch_bounds__(256) k_unpack(const u64* __restrict__ own, const u64* __restrict__ opp,
+                                                const int8_t* __restrict__ players, int own_stride, int8_t* __restrict__ states,
+                                                int64_t n)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nw) {
+        const u64 o = own[i * own_stride], p = opp[i * own_stride];
+        const int pl = players ? players[i] : 1;
+        // two cells per lane, written as one 16-bit store
+        const int a = 2 * lane;
+        const int v0 = ((o >> a) & 1) ? pl : (((p >> a) & 1) ? -pl : 0);
+        const int v1 = ((o >> (a + 1)) & 1) ? pl : (((p >> (a + 1)) & 1) ? -pl : 0);
+        reinterpret_cast<uint16_t*>(states + i * 64)[lane] = (uint16_t)((v0 & 0xff) | ((v1 & 0xff) << 8));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_valid_moves_i8(const int8_t* __restrict__ states, const int8_t* __restrict__ players,
+                                                       uint8_t* __restrict__ out, int64_t n)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nw) {
+        u64 o, p;
+        warp_pack(states + i * 64, players[i], lane, o, p);
+        const u64 m = legal_moves(o, p);
+        uint8_t* dst = out + i * OTH_NUM_ACTIONS;
+        dst[lane] = (uint8_t)((m >> lane) & 1);
+        dst[lane + 32] = (uint8_t)((m >> (lane + 32)) & 1);
+        if (lane == 0) dst[64] = (uint8_t)(m == 0);  // pass iff no board move (envs/othello.py:401-403)
+    }
+}
+
+__global__ void __launch_bounds__(256) k_next_state_i8(const int8_t* __restrict__ states, const int32_t* __restrict__ actions,
+                                                       const int8_t* __restrict__ players, int8_t* __restrict__ out,
+                                                       uint8_t* __restrict__ out_flags, int64_t n)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nw) {
+        u64 o, p;
+        const int pl = players[i];
+        warp_pack(states + i * 64, pl, lane, o, p);
+        const int a = actions[i];
+        unsigned fl = 0;
+        u64 f = 0;
+        if (a != OTH_PASS) {  // pass copies the board unchecked (envs/othello.py:415-416)
+            const u64 x = (a >= 0 && a < 64) ? (1ULL << a) : 0ULL;
+            f = (x & ~(o | p)) ? flips(o, p, x) : 0ULL;
+            if (f == 0) fl = OTH_F_ILLEGAL;
+            else {
+                o |= x | f;
+                p &= ~f;
+            }
+        }
+        const int c = 2 * lane;  // absolute colours: player's discs stay = player
+        const int v0 = ((o >> c) & 1) ? pl : (((p >> c) & 1) ? -pl : 0);
+        const int v1 = ((o >> (c + 1)) & 1) ? pl : (((p >> (c + 1)) & 1) ? -pl : 0);
+        reinterpret_cast<uint16_t*>(out + i * 64)[lane] = (uint16_t)((v0 & 0xff) | ((v1 & 0xff) << 8));
+        if (lane == 0 && out_flags) out_flags[i] = (uint8_t)fl;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_value_terminated_i8(const int8_t* __restrict__ states, const int8_t* __restrict__ players,
+                                                             int8_t* __restrict__ values, uint8_t* __restrict__ terms, int64_t n)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nw) {
+        u64 o, p;
+        warp_pack(states + i * 64, players[i], lane, o, p);
+        int v;
+        const int st = position_status(o, p, legal_moves(o, p), &v);
+        if (lane == 0) {
+            values[i] = (int8_t)v;
+            terms[i] = (uint8_t)(st == 2);
+        }
+    }
+}
+
+// Dihedral image: out[r][c] = in[src(r,c)], np.rot90 k times then np.fliplr.
+__global__ void __launch_bounds__(256) k_symmetry(const int8_t* __restrict__ states, const float* __restrict__ pis,
+                                                  const int32_t* __restrict__ ks, const uint8_t* __restrict__ flips_,
+                                                  float* __restrict__ out_s, float* __restrict__ out_pi, int64_t n)
+{
+    const int64_t total = n * 65;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t i = t / 65;
+        const int e = (int)(t - i * 65);
+        if (e == 64) {
+            if (out_pi) out_pi[i * 65 + 64] = pis[i * 65 + 64];
+            continue;
+        }
+        int r = e >> 3, c = e & 7;
+        if (flips_[i]) c = 7 - c;
+        const int k = ks[i] & 3;
+        for (int q = 0; q < k; q++) {
+            const int nr = c, nc = 7 - r;
+            r = nr;
+            c = nc;
+        }
+        const int src = r * 8 + c;
+        if (out_s) out_s[i * 64 + e] = (float)states[i * 64 + src];
+        if (out_pi) out_pi[i * 65 + e] = pis[i * 65 + src];
+    }
+}
+
+// canonical packed boards [n][2] -> int8 [n,64] (+1 own / -1 opp)
+extern "C" int oth_unpack_canonical(const uint64_t* boards, int8_t* states, int64_t n, void* stream)
+{
+    if (n <= 0) return OTH_OK;
+    k_unpack<<<grid_for(n * 32, 256), 256, 0, (cudaStream_t)stream>>>((const u64*)boards, (const u64*)boards + 1, nullptr, 2,
+                                                                      states, n);
+    return cuda_status(cudaGetLastError());
+}
+
+// INT32 ALU probe: 8 independent chains of LOP3 + IADD3 per thread.
+__global__ void __launch_bounds__(256) k_int32_probe(unsigned* __restrict__ out, int iters, unsigned b, unsigned c)
+{
+    unsigned a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+#define STEP(x)                                                                               \
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(b), "r"(c));                 \
+    asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(c));
+            STEP(a0) STEP(a1) STEP(a2) STEP(a3) STEP(a4) STEP(a5) STEP(a6) STEP(a7)
+#undef STEP
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
+// ----------------------------------------------------------------- C ABI --
+
+static char g_cuda_err[256] = "";
+
+namespace oth {
+int cuda_status(cudaError_t e)
+{
+    if (e == cudaSuccess) return OTH_OK;
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? OTH_E_NO_DEVICE : OTH_E_CUDA;
+}
+
+int sm_count()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+// grid sized in multiples of the SM count (148 on B200), capped by the work
+int grid_for(int64_t threads, int block)
+{
+    const int64_t need = (threads + block - 1) / block;
+    const int64_t full = (int64_t)sm_count() * 8;
+    if (need <= 0) return 1;
+    if (need >= full) return (int)full;
+    const int64_t sms = sm_count();
+    return (int)(need <= sms ? need : ((need + sms - 1) / sms) * sms);
+}
+}  // namespace oth
+
+extern "C" int oth_abi_version(void) { return OTH_ABI_VERSION; }
+
+extern "C" const char* oth_error_string(int code)
+{
+    switch (code) {
+    case OTH_OK: return "ok";
+    case OTH_E_CUDA: return "CUDA runtime error";
+    case OTH_E_ARG: return "bad argument";
+    case OTH_E_ILLEGAL: return "Illegal move";
+    case OTH_E_NO_DEVICE: return "no CUDA device (libothello_b200 has no CPU fallback)";
+    default: return "unknown error";
+    }
+}
+
+extern "C" const char* oth_last_cuda_error(void) { return g_cuda_err; }
+
+extern "C" int oth_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int oth_legal_moves(const uint64_t* own, const uint64_t* opp, uint64_t* out, int64_t n, void* stream)
+{
+    if (n < 0 || (n > 0 && (!own || !opp || !out))) return OTH_E_ARG;
+    if (n == 0) return OTH_OK;
+    if ((((uintptr_t)own | (uintptr_t)opp | (uintptr_t)out) & 15) != 0) return OTH_E_ARG;  // 128-bit access
+    k_legal_moves<<<grid_for((n + 1) / 2, 256), 256, 0, (cudaStream_t)stream>>>((const u64*)own, (const u64*)opp, (u64*)out, n);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int oth_step(const uint64_t* own, const uint64_t* opp, const uint8_t* action, uint64_t* out_own, uint64_t* out_opp,
+                        uint64_t* out_moves, uint8_t* out_flags, int64_t n, void* stream)
+{
+    if (n < 0 || (n > 0 && (!own || !opp || !action || !out_own || !out_opp))) return OTH_E_ARG;
+    if (n == 0) return OTH_OK;
+    k_step<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const u64*)own, (const u64*)opp, action, (u64*)out_own,
+                                                               (u64*)out_opp, (u64*)out_moves, out_flags, n);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int oth_rollout(uint64_t seed, uint64_t game_id_base, int64_t n_games, int32_t* out_score, int32_t* out_plies,
+                           uint64_t* out_final, int64_t n_trace, uint8_t* trace_actions, uint64_t* trace_moves,
+                           unsigned long long* counters, void* stream)
+{
+    if (n_games < 0 || n_trace < 0 || n_trace > n_games) return OTH_E_ARG;
+    if (n_games == 0) return OTH_OK;
+    k_rollout<<<grid_for(n_games, 256), 256, 0, (cudaStream_t)stream>>>(seed, game_id_base, n_games, out_score, out_plies,
+                                                                       (u64*)out_final, n_trace, trace_actions, (u64*)trace_moves,
+                                                                       counters);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int oth_pack_states(const int8_t* states, const int8_t* players, uint64_t* own, uint64_t* opp, int64_t n, void* stream)
+{
+    if (n < 0 || (n > 0 && (!states || !own || !opp))) return OTH_E_ARG;
+    if (n == 0) return OTH_OK;
+    k_pack<<<grid_for(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(states, players, (u64*)own, (u64*)opp, n);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int oth_unpack_states(const uint64_t* own, const uint64_t* opp, const int8_t* players, int8_t* states, int64_t n,
+                                 void* stream)
+{
+    if (n < 0 || (n > 0 && (!states || !own || !opp))) return OTH_E_ARG;
+    if (n == 0) return OTH_OK;
+    k_unpack<<<grid_for(n * 32, 256), 256, 0, (cudaStream_t)stream>>>((const u64*)own, (const u64*)opp, players, 1, states, n);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int oth_valid_moves_i8(const int8_t* states, const int8_t* players, uint8_t* out_masks, int64_t n, void* stream)
+{
+    if (n < 0 || (n > 0 && (!states || !players || !out_masks))) return OTH_E_ARG;
+    if (n == 0) return OTH_OK;
+    k_valid_moves_i8<<<grid_for(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(states, players, out_masks, n);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int oth_symmetry(const int8_t* states, const float* pis, const int32_t* ks, const uint8_t* flips_, float* out_states,
+                            float* out_pis, int64_t n, void* stream)
+{
+    if (n < 0 || (n > 0 && (!states || !pis || !ks || !flips_))) return OTH_E_ARG;
+    if (n == 0) return OTH_OK;
+    k_symmetry<<<grid_for(n * 65, 256), 256, 0, (cudaStream_t)stream>>>(states, pis, ks, flips_, out_states, out_pis, n);
+    return cuda_status(cudaGetLastError());
+}
+
+// ------------------------------------------------------ host-buffer forms --
+
+namespace {
+struct Scratch {  // grow-only device staging for the oth_host_* calls (not thread-safe)
+    void* p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int get(int i, size_t bytes, void** out)
+    {
+        if (bytes > cap[i]) {
+            if (p[i]) cudaFree(p[i]);
+            p[i] = nullptr;
+            cap[i] = 0;
+            size_t want = bytes < 4096 ? 4096 : bytes + bytes / 2;
+            cudaError_t e = cudaMalloc(&p[i], want);
+            if (e != cudaSuccess) return cuda_status(e);
+            cap[i] = want;
+        }
+        *out = p[i];
+        return OTH_OK;
+    }
+};
+Scratch g_scr;
+
+#define CK(x)                          \
+    do {                               \
+        int _rc = (x);                 \
+        if (_rc != OTH_OK) return _rc; \
+    } while (0)
+#define CU(x) CK(cuda_status(x))
+}  // namespace
+
+extern "C" int oth_host_valid_moves(const int8_t* states, const int8_t* players, uint8_t* out_masks, int64_t n)
+{
+    if (n < 0 || (n > 0 && (!states || !players || !out_masks))) return OTH_E_ARG;
+    if (n == 0) return OTH_OK;
+    void *ds, *dp, *dm;
+    CK(g_scr.get(0, n * 64, &ds));
+    CK(g_scr.get(1, n, &dp));
+    CK(g_scr.get(2, n * 65, &dm));
+    CU(cudaMemcpyAsync(ds, states, n * 64, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(dp, players, n, cudaMemcpyHostToDevice, 0));
+    CK(oth_valid_moves_i8((const int8_t*)ds, (const int8_t*)dp, (uint8_t*)dm, n, 0));
+    CU(cudaMemcpyAsync(out_masks, dm, n * 65, cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    return OTH_OK;
+}
+
+extern "C" int oth_host_next_state(const int8_t* states, const int32_t* actions, const int8_t* players, int8_t* out_states,
+                                   uint8_t* out_flags, int64_t n)
+{
+    if (n < 0 || (n > 0 && (!states || !players || !actions || !out_states || !out_flags))) return OTH_E_ARG;
+    if (n == 0) return OTH_OK;
+    void *ds, *dp, *da, *dout, *df;
+    CK(g_scr.get(0, n * 64, &ds));
+    CK(g_scr.get(1, n, &dp));
+    CK(g_scr.get(2, n * 4, &da));
+    CK(g_scr.get(3, n * 64, &dout));
+    CK(g_scr.get(4, n, &df));
+    CU(cudaMemcpyAsync(ds, states, n * 64, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(dp, players, n, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(da, actions, n * 4, cudaMemcpyHostToDevice, 0));
+    k_next_state_i8<<<grid_for(n * 32, 256), 256>>>((const int8_t*)ds, (const int32_t*)da, (const int8_t*)dp, (int8_t*)dout,
+                                                    (uint8_t*)df, n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_states, dout, n * 64, cudaMemcpyDeviceToHost, 0));
+    CU(cudaMemcpyAsync(out_flags, df, n, cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    for (int64_t i = 0; i < n; i++)
+        if (out_flags[i] & OTH_F_ILLEGAL) return OTH_E_ILLEGAL;
+    return OTH_OK;
+}
+
+extern "C" int oth_host_value_terminated(const int8_t* states, const int8_t* players, int8_t* out_values, uint8_t* out_terms,
+                                         int64_t n)
+{
+    if (n < 0 || (n > 0 && (!states || !players || !out_values || !out_terms))) return OTH_E_ARG;
+    if (n == 0) return OTH_OK;
+    void *ds, *dp, *dv, *dt;
+    CK(g_scr.get(0, n * 64, &ds));
+    CK(g_scr.get(1, n, &dp));
+    CK(g_scr.get(2, n, &dv));
+    CK(g_scr.get(3, n, &dt));
+    CU(cudaMemcpyAsync(ds, states, n * 64, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(dp, players, n, cudaMemcpyHostToDevice, 0));
+    k_value_terminated_i8<<<grid_for(n * 32, 256), 256>>>((const int8_t*)ds, (const int8_t*)dp, (int8_t*)dv, (uint8_t*)dt, n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_values, dv, n, cudaMemcpyDeviceToHost, 0));
+    CU(cudaMemcpyAsync(out_terms, dt, n, cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    return OTH_OK;
+}
+
+extern "C" int oth_host_symmetry(const int8_t* states, const float* pis, const int32_t* ks, const uint8_t* flips_, float* out_states,
+                                 float* out_pis, int64_t n)
+{
+    if (n < 0 || (n > 0 && (!states || !pis || !ks || !flips_ || !out_states || !out_pis))) return OTH_E_ARG;
+    if (n == 0) return OTH_OK;
+    void *ds, *dpi, *dk, *df, *dos, *dop;
+    CK(g_scr.get(0, n * 64, &ds));
+    CK(g_scr.get(1, n * 65 * 4, &dpi));
+    CK(g_scr.get(2, n * 4, &dk));
+    CK(g_scr.get(3, n, &df));
+    CK(g_scr.get(4, n * 64 * 4, &dos));
+    CK(g_scr.get(5, n * 65 * 4, &dop));
+    CU(cudaMemcpyAsync(ds, states, n * 64, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(dpi, pis, n * 65 * 4, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(dk, ks, n * 4, cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(df, flips_, n, cudaMemcpyHostToDevice, 0));
+    CK(oth_symmetry((const int8_t*)ds, (const float*)dpi, (const int32_t*)dk, (const uint8_t*)df, (float*)dos, (float*)dop, n, 0));
+    CU(cudaMemcpyAsync(out_states, dos, n * 64 * 4, cudaMemcpyDeviceToHost, 0));
+    CU(cudaMemcpyAsync(out_pis, dop, n * 65 * 4, cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    return OTH_OK;
+}
+
+extern "C" int oth_host_rollout(uint64_t seed, uint64_t game_id_base, int64_t n_games, int32_t* out_score, int32_t* out_plies,
+                                uint64_t* out_final, int64_t n_trace, uint8_t* trace_actions, uint64_t* trace_moves,
+                                unsigned long long* total_plies, float* kernel_ms)
+{
+    if (n_games <= 0 || n_trace < 0 || n_trace > n_games) return OTH_E_ARG;
+    void *dsc, *dpl, *dfin, *dta = nullptr, *dtm = nullptr, *dcnt;
+    CK(g_scr.get(0, n_games * 4, &dsc));
+    CK(g_scr.get(1, n_games * 4, &dpl));
+    CK(g_scr.get(2, n_games * 16, &dfin));
+    if (n_trace) {
+        CK(g_scr.get(3, n_trace * OTH_MAX_PLIES, &dta));
+        CK(g_scr.get(4, n_trace * OTH_MAX_PLIES * 8, &dtm));
+    }
+    CK(g_scr.get(5, 64, &dcnt));
+    CU(cudaMemsetAsync(dcnt, 0, 64, 0));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, 0));
+    int rc = oth_rollout(seed, game_id_base, n_games, (int32_t*)dsc, (int32_t*)dpl, (uint64_t*)dfin, n_trace, (uint8_t*)dta,
+                         (uint64_t*)dtm, (unsigned long long*)dcnt, 0);
+    CU(cudaEventRecord(e1, 0));
+    if (rc != OTH_OK) return rc;
+    if (out_score) CU(cudaMemcpyAsync(out_score, dsc, n_games * 4, cudaMemcpyDeviceToHost, 0));
+    if (out_plies) CU(cudaMemcpyAsync(out_plies, dpl, n_games * 4, cudaMemcpyDeviceToHost, 0));
+    if (out_final) CU(cudaMemcpyAsync(out_final, dfin, n_games * 16, cudaMemcpyDeviceToHost, 0));
+    if (n_trace && trace_actions) CU(cudaMemcpyAsync(trace_actions, dta, n_trace * OTH_MAX_PLIES, cudaMemcpyDeviceToHost, 0));
+    if (n_trace && trace_moves) CU(cudaMemcpyAsync(trace_moves, dtm, n_trace * OTH_MAX_PLIES * 8, cudaMemcpyDeviceToHost, 0));
+    if (total_plies) CU(cudaMemcpyAsync(total_plies, dcnt, 8, cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    if (kernel_ms) CU(cudaEventElapsedTime(kernel_ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return OTH_OK;
+}
+
+extern "C" int oth_host_int32_peak(double* out_ips, float* kernel_ms)
+{
+    const int blocks = sm_count() * 8, threads = 256, iters = 2048;
+    void* d;
+    CK(g_scr.get(6, (size_t)blocks * threads * 4, &d));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(e0, 0));
+        k_int32_probe<<<blocks, threads>>>((unsigned*)d, iters, 0x12345u + rep, 0x9e3779b9u);
+        CU(cudaEventRecord(e1, 0));
+        CU(cudaStreamSynchronize(0));
+        CU(cudaGetLastError());
+        float ms;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double instr = (double)blocks * threads * (double)iters * 8.0 * 8.0 * 2.0;
+    if (out_ips) *out_ips = instr / (best * 1e-3);
+    if (kernel_ms) *kernel_ms = best;
+    return OTH_OK;
+}

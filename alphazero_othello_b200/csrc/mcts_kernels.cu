@@ -1,0 +1,1164 @@
+// Batched MCTS self-play engine for B200 (sm_100a).
+//
+// One group of LANES threads (a warp by default) owns one game slot.  The tree
+// of a slot lives in two flat arenas in HBM (32-byte node records + 16-byte
+// boards); children of a node are contiguous and in ascending action order,
+// so PUCT selection is one coalesced 2x128-bit load per lane and a shuffle
+// arg-max.  Re-rooting (MCTS.make_move) compacts the kept subtree into the
+// other arena, breadth first.
+//
+// Semantics restated from the reference (num_threads = 1):
+//   Node / PUCT / expand / backup    MCTS_model.py:46-169
+//   MCTS.policy_improve_step etc.    MCTS_model.py:172-395
+//   one_self_play, lambda-returns    self_play_worker.py:8-88
+// including numpy>=2 promotion: float32 PUCT for ordinary nodes, float64 at a
+// Dirichlet-noised root, float64 value sums, numpy's 8-lane pairwise sums.
+// Compiled with --fmad=false; the rounding-critical steps also use the
+// explicit *_rn intrinsics.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/othello_b200.h"
+#include "bitboard.cuh"
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace cg = cooperative_groups;
+using namespace oth;
+
+namespace {
+
+constexpr int kBlock = 128;
+constexpr uint64_t kSaltNoise = 0x6e6f697365ULL;  // Philox purposes
+constexpr uint32_t kPurposeMove = 1, kPurposeTie = 2;
+
+struct __align__(32) Node {
+    double W;             // value_sum (MCTS_model.py:84), float64
+    float prior;          // float32 prior (float64 copy in root_prior64 at a noised root)
+    int32_t N;            // visit_count
+    int32_t first_child;  // -1: leaf
+    uint32_t meta;        // nchild | action << 8 | flags << 16 | (terminal_value & 0xff) << 24
+    u64 moves;            // legal set of the side to move at this node (Node.valid_mask :96)
+};
+static_assert(sizeof(Node) == 32, "node record must be one 32-byte sector");
+
+constexpr uint32_t kFlagTerminal = 1u;
+
+__device__ __forceinline__ int meta_nchild(uint32_t m) { return (int)(m & 0xffu); }
+__device__ __forceinline__ int meta_action(uint32_t m) { return (int)((m >> 8) & 0xffu); }
+__device__ __forceinline__ uint32_t meta_flags(uint32_t m) { return (m >> 16) & 0xffu; }
+__device__ __forceinline__ int meta_tvalue(uint32_t m) { return (int)(int8_t)(m >> 24); }
+__device__ __forceinline__ uint32_t make_meta(int nchild, int action, uint32_t flags, int tv)
+{
+    return (uint32_t)nchild | ((uint32_t)action << 8) | (flags << 16) | (((uint32_t)tv & 0xffu) << 24);
+}
+
+// Two 128-bit accesses per record.  Plain (coherent) loads: records are
+// rewritten by this group within the same launch.
+__device__ __forceinline__ Node load_node(const Node* p)
+{
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    const uint4 b = *(reinterpret_cast<const uint4*>(p) + 1);
+    Node n;
+    n.W = __hiloint2double((int)a.y, (int)a.x);
+    n.prior = __uint_as_float(a.z);
+    n.N = (int)a.w;
+    n.first_child = (int)b.x;
+    n.meta = b.y;
+    n.moves = ((u64)b.w << 32) | b.z;
+    return n;
+}
+
+__device__ __forceinline__ void store_node(Node* p, const Node& n)
+{
+    uint4 a, b;
+    a.x = (unsigned)__double2loint(n.W);
+    a.y = (unsigned)__double2hiint(n.W);
+    a.z = __float_as_uint(n.prior);
+    a.w = (unsigned)n.N;
+    b.x = (unsigned)n.first_child;
+    b.y = n.meta;
+    b.z = (unsigned)n.moves;
+    b.w = (unsigned)(n.moves >> 32);
+    *reinterpret_cast<uint4*>(p) = a;
+    *(reinterpret_cast<uint4*>(p) + 1) = b;
+}
+
+struct Params {
+    oth_mcts_config cfg;
+    Node* nodes;
+    ulonglong2* boards;
+    oth_mcts_ctl* ctl;
+    int* path;
+    double* root_prior64;
+    double* noise;
+    double* u_move;
+    double* u_tie;
+    ulonglong2* traj_board;
+    float* traj_pi;
+    double* traj_rootv;
+    int* traj_meta;
+    ulonglong2* out_board;
+    float* out_pi;
+    double* out_value;
+    long long* out_meta;
+    long long* out_games;
+    unsigned long long* counters;
+    const float* priors;
+    const float* values;
+    float* nn_input;
+    float c_puct_f32;
+};
+
+// per-group scratch in shared memory
+struct __align__(16) Scratch {
+    double pri64[OTH_NUM_ACTIONS + 1];
+    float pri[OTH_NUM_ACTIONS + 3];
+    int path[256];
+};
+
+enum { CNT_LOCAL = 16 };
+
+template <int LANES>
+struct Ctx {
+    cg::thread_block_tile<LANES> tile;
+    const Params& P;
+    Scratch& S;
+    int lane;
+    int slot;
+    Node* N;        // current arena
+    ulonglong2* B;
+    oth_mcts_ctl c;
+    unsigned long long cnt[CNT_LOCAL];
+
+    __device__ Ctx(cg::thread_block_tile<LANES> t, const Params& p, Scratch& s) : tile(t), P(p), S(s), lane(t.thread_rank()), slot(0)
+    {
+#pragma unroll
+        for (int i = 0; i < CNT_LOCAL; i++) cnt[i] = 0;
+    }
+
+    __device__ __forceinline__ void bind_arena()
+    {
+        const size_t base = ((size_t)slot * 2 + (size_t)c.arena) * (size_t)P.cfg.node_cap;
+        N = P.nodes + base;
+        B = P.boards + base;
+    }
+
+    __device__ __forceinline__ void fail(int bit)
+    {
+        c.error |= bit;
+        c.phase = OTH_PH_ERROR;
+    }
+
+    // numpy pairwise add.reduce over 65 float32 in S.pri (MCTS_model.py:347, :259)
+    __device__ __forceinline__ float np_sum65_f32()
+    {
+        float r = 0.0f;
+        if (lane < 8) {
+            r = S.pri[lane];
+#pragma unroll
+            for (int i = 1; i < 8; i++) r = __fadd_rn(r, S.pri[8 * i + lane]);
+        }
+        r = __fadd_rn(r, tile.shfl_xor(r, 1));
+        r = __fadd_rn(r, tile.shfl_xor(r, 2));
+        r = __fadd_rn(r, tile.shfl_xor(r, 4));
+        r = tile.shfl(r, 0);
+        return __fadd_rn(r, S.pri[64]);
+    }
+
+    __device__ __forceinline__ double np_sum65_f64()
+    {
+        double r = 0.0;
+        if (lane < 8) {
+            r = S.pri64[lane];
+#pragma unroll
+            for (int i = 1; i < 8; i++) r = __dadd_rn(r, S.pri64[8 * i + lane]);
+        }
+        r = __dadd_rn(r, tile.shfl_xor(r, 1));
+        r = __dadd_rn(r, tile.shfl_xor(r, 2));
+        r = __dadd_rn(r, tile.shfl_xor(r, 4));
+        r = tile.shfl(r, 0);
+        return __dadd_rn(r, S.pri64[64]);
+    }
+
+    // canonical plane of the side to move: +1 own, -1 opp (Models.py:16)
+    __device__ __forceinline__ void write_nn_input(u64 own, u64 opp)
+    {
+        float* dst = P.nn_input + (size_t)slot * 64;
+        for (int e = lane; e < 64; e += LANES) dst[e] = ((own >> e) & 1) ? 1.0f : (((opp >> e) & 1) ? -1.0f : 0.0f);
+    }
+
+    // ------------------------------------------------------------ stubs --
+    __device__ __forceinline__ u64 mix64(u64 x)
+    {
+        x ^= x >> 33;
+        x *= 0xff51afd7ed558ccdULL;
+        x ^= x >> 33;
+        x *= 0xc4ceb9fe1a85ec53ULL;
+        x ^= x >> 33;
+        return x;
+    }
+
+    // Device twins of oracle/othello_oracle.c orc_stub_a/b/h: raw priors to S.pri, value returned.
+    __device__ double eval_stub(u64 own, u64 opp)
+    {
+        double value = 0.0;
+        const int kind = P.cfg.eval_kind;
+        if (kind == OTH_EVAL_STUB_A) {
+            const float v = (float)(1.0 / 65.0);
+            for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri[a] = v;
+        } else if (kind == OTH_EVAL_STUB_B) {
+            long long h = 0;
+            for (int e = lane; e < 64; e += LANES) h += ((own >> e) & 1) ? (e + 1) : (((opp >> e) & 1) ? -(e + 1) : 0);
+            for (int o = LANES / 2; o; o >>= 1) h += tile.shfl_xor(h, o);
+            float sum = 0.0f;  // small integers: exact in any order
+            for (int a = 0; a < OTH_NUM_ACTIONS; a++) {
+                long long t = (7LL * a + h) % 11;
+                if (t < 0) t += 11;
+                sum += (float)(t + 1);
+            }
+            for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) {
+                long long t = (7LL * a + h) % 11;
+                if (t < 0) t += 11;
+                S.pri[a] = __fdiv_rn((float)(t + 1), sum);
+            }
+            long long t = h % 17;
+            if (t < 0) t += 17;
+            value = (double)(t - 8) / 16.0;
+        } else {  // OTH_EVAL_STUB_H: hashed in the reference's bit numbering (bit = 63 - idx)
+            const u64 h = mix64(__brevll(own) ^ mix64(__brevll(opp) ^ P.cfg.stub_salt));
+            int part = 0;
+            for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) part += 1 + (int)(mix64(h + (u64)a) % 251ULL);
+            for (int o = LANES / 2; o; o >>= 1) part += tile.shfl_xor(part, o);
+            const float sum = (float)part;
+            for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES)
+                S.pri[a] = __fdiv_rn((float)(1 + (int)(mix64(h + (u64)a) % 251ULL)), sum);
+            const int v = (int)(mix64(h ^ 0x9e3779b97f4a7c15ULL) % 2001ULL) - 1000;
+            value = (double)__fdiv_rn((float)v, 1000.0f);
+        }
+        tile.sync();
+        return value;
+    }
+
+    // ------------------------------------------------- Dirichlet noise --
+    // np.random.dirichlet([alpha]*65) (MCTS_model.py:341) drawn from Philox:
+    // Marsaglia-Tsang gammas, normalised.  The draw is written to P.noise so
+    // a checker can replay it; with inject_random it is read from there.
+    __device__ void make_noise()
+    {
+        double* nz = P.noise + (size_t)slot * OTH_NUM_ACTIONS;
+        if (!P.cfg.inject_random) {
+            const double alpha = P.cfg.dirichlet_alpha;
+            const double a = alpha < 1.0 ? alpha + 1.0 : alpha;
+            const double d = a - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * d);
+            for (int e = lane; e < OTH_NUM_ACTIONS; e += LANES) {
+                double g = d;
+                for (uint32_t k = 0; k < 256; k++) {
+                    const Philox4 r = philox4x32_10(P.cfg.seed ^ kSaltNoise, (uint64_t)c.game_id, (uint32_t)e, k);
+                    const double u1 = ((double)r.x + 1.0) * (1.0 / 4294967296.0);
+                    const double u2 = (double)r.y * (1.0 / 4294967296.0);
+                    const double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+                    double v = 1.0 + cc * x;
+                    if (v <= 0.0) continue;
+                    v = v * v * v;
+                    const double u = ((double)r.z + 0.5) * (1.0 / 4294967296.0);
+                    if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) {
+                        g = d * v;
+                        if (alpha < 1.0) g *= pow(((double)r.w + 0.5) * (1.0 / 4294967296.0), 1.0 / alpha);
+                        break;
+                    }
+                }
+                S.pri64[e] = g;
+            }
+            tile.sync();
+            double s = 0.0;
+            for (int e = 0; e < OTH_NUM_ACTIONS; e++) s += S.pri64[e];
+            tile.sync();
+            for (int e = lane; e < OTH_NUM_ACTIONS; e += LANES) nz[e] = S.pri64[e] / s;
+            tile.sync();
+        }
+    }
+
+    // -------------------------------------------------------- expansion --
+    // MCTS._expand_and_evaluate (MCTS_model.py:325-360) given raw float32
+    // priors in S.pri: noise mix (root only), mask, pairwise-sum normalise,
+    // create every child in ascending action order (Node.expand :146-158,
+    // Node.__init__ :68-108 -- child boards, legal sets and terminal values
+    // are computed here, one child per lane).
+    __device__ bool expand(int leaf, bool root_init)
+    {
+        const Node lf = load_node(N + leaf);
+        const ulonglong2 lb = B[leaf];
+        const u64 own = lb.x, opp = lb.y;
+        const u64 M = lf.moves;
+        const bool is_pass = (M == 0);
+        const int nchild = is_pass ? 1 : __popcll(M);
+        const int fc = c.top;
+        if (fc + nchild > P.cfg.node_cap) {
+            fail(OTH_ERR_NODE_OVERFLOW);
+            return false;
+        }
+        const bool f64 = root_init && P.cfg.dirichlet_epsilon > 0.0;
+        if (f64) {
+            make_noise();
+            const double* nz = P.noise + (size_t)slot * OTH_NUM_ACTIONS;
+            const double eps = P.cfg.dirichlet_epsilon;
+            const float om = (float)(1.0 - eps);  // (1-eps)*priors stays float32 (NEP 50)
+            for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) {
+                const float t = __fmul_rn(om, S.pri[a]);
+                double v = __dadd_rn((double)t, __dmul_rn(eps, nz[a]));
+                const bool valid = a < 64 ? ((M >> a) & 1) : is_pass;
+                S.pri64[a] = valid ? v : __dmul_rn(v, 0.0);
+            }
+            tile.sync();
+            const double s = np_sum65_f64();
+            tile.sync();
+            if (s > 1e-12)
+                for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri64[a] = __ddiv_rn(S.pri64[a], s);
+        } else {
+            for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) {
+                const bool valid = a < 64 ? ((M >> a) & 1) : is_pass;
+                if (!valid) S.pri[a] = __fmul_rn(S.pri[a], 0.0f);
+            }
+            tile.sync();
+            const float s = np_sum65_f32();
+            tile.sync();
+            if (s > (float)1e-12)
+                for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri[a] = __fdiv_rn(S.pri[a], s);
+        }
+        tile.sync();
+        for (int i = lane; i < nchild; i += LANES) {
+            const int a = is_pass ? OTH_PASS : nth_set_bit(M, i);
+            const u64 f = is_pass ? 0ULL : flips(own, opp, 1ULL << a);
+            const Board cb = apply_move(own, opp, a, f);
+            Node ch;
+            ch.W = 0.0;
+            ch.N = 0;
+            ch.first_child = -1;
+            ch.moves = legal_moves(cb.own, cb.opp);
+            int tv;
+            const int st = position_status(cb.own, cb.opp, ch.moves, &tv);
+            ch.meta = make_meta(0, a, st == 2 ? kFlagTerminal : 0u, tv);
+            if (f64) {
+                P.root_prior64[(size_t)slot * OTH_MAX_CHILDREN + i] = S.pri64[a];
+                ch.prior = (float)S.pri64[a];
+            } else {
+                ch.prior = S.pri[a];
+            }
+            store_node(N + fc + i, ch);
+            B[fc + i] = make_ulonglong2(cb.own, cb.opp);
+        }
+        if (lane == 0) {
+            Node* p = N + leaf;
+            p->first_child = fc;
+            p->meta = (lf.meta & ~0xffu) | (uint32_t)nchild;
+        }
+        c.top = fc + nchild;
+        if (f64) c.flags |= 2;
+        cnt[OTH_CNT_NODES] += (lane == 0) ? nchild : 0;
+        tile.sync();
+        return true;
+    }
+
+    // Node.backpropagate (MCTS_model.py:160-169) along S.path[0..depth).
+    __device__ __forceinline__ void backup(int depth, double value)
+    {
+        tile.sync();
+        for (int d = lane; d < depth; d += LANES) {
+            Node* p = N + S.path[d];
+            const double sv = ((depth - 1 - d) & 1) ? -value : value;
+            p->N += 1;
+            p->W = __dadd_rn(p->W, sv);
+        }
+        tile.sync();
+    }
+
+    // MCTS._simulate's descent (MCTS_model.py:372-392) with _select_child /
+    // _get_ucb_score (:362-370, :129-139).  Returns 0 = reached a leaf,
+    // 1 = reached a terminal node, -1 = error.  The parent's own virtual
+    // visit is the "+1" under the square root; children carry none.
+    __device__ int descend(int& leaf, int& depth, Node& nd)
+    {
+        int cur = c.root;
+        nd = load_node(N + cur);
+        depth = 0;
+        const double cp64 = P.cfg.c_puct;
+        const float cp32 = P.c_puct_f32;
+        for (;;) {
+            if (depth >= P.cfg.path_cap) {
+                fail(OTH_ERR_PATH_OVERFLOW);
+                return -1;
+            }
+            if (lane == 0) S.path[depth] = cur;
+            depth++;
+            leaf = cur;
+            if (meta_flags(nd.meta) & kFlagTerminal) return 1;
+            if (nd.first_child < 0) return 0;
+            const int fc = nd.first_child, nchild = meta_nchild(nd.meta);
+            const double sq = sqrt((double)(nd.N + 1) + 1e-8);
+            const float sq32 = (float)sq;
+            const bool f64 = (depth == 1) && (c.flags & 2);
+            double bs = -INFINITY;
+            int bi = 0x7fffffff;
+            int k_N = 0, k_fc = -1;
+            uint32_t k_meta = 0;
+            u64 k_moves = 0;
+            for (int i = lane; i < nchild; i += LANES) {
+                const Node ch = load_node(N + fc + i);
+                const double q = ch.N ? -__ddiv_rn(ch.W, (double)ch.N) : -0.0;
+                double sc;
+                if (!f64) {
+                    float u = __fmul_rn(cp32, ch.prior);
+                    u = __fmul_rn(u, sq32);
+                    u = __fdiv_rn(u, (float)(1 + ch.N));
+                    sc = (double)__fadd_rn((float)q, u);
+                } else {
+                    double u = __dmul_rn(cp64, P.root_prior64[(size_t)slot * OTH_MAX_CHILDREN + i]);
+                    u = __dmul_rn(u, sq);
+                    u = __ddiv_rn(u, (double)(1 + ch.N));
+                    sc = __dadd_rn(q, u);
+                }
+                if (sc > bs) {  // ascending i: the first maximum wins (:366-369)
+                    bs = sc;
+                    bi = i;
+                    k_N = ch.N;
+                    k_fc = ch.first_child;
+                    k_meta = ch.meta;
+                    k_moves = ch.moves;
+                }
+            }
+#pragma unroll
+            for (int o = LANES / 2; o; o >>= 1) {
+                const double os = tile.shfl_xor(bs, o);
+                const int oi = tile.shfl_xor(bi, o);
+                if (os > bs || (os == bs && oi < bi)) {
+                    bs = os;
+                    bi = oi;
+                }
+            }
+            const int src = bi % LANES;
+            nd.N = tile.shfl(k_N, src);
+            nd.first_child = tile.shfl(k_fc, src);
+            nd.meta = tile.shfl(k_meta, src);
+            nd.moves = tile.shfl(k_moves, src);
+            cur = fc + bi;
+            if (lane == 0) {
+                cnt[OTH_CNT_LEVELS] += 1;
+                cnt[OTH_CNT_CHILDREN] += nchild;
+            }
+        }
+    }
+
+    // --------------------------------------------------------- new game --
+    __device__ void init_tree(u64 own, u64 opp, int player)
+    {
+        c.arena = 0;
+        bind_arena();
+        if (lane == 0) {
+            Node r;
+            r.W = 0.0;
+            r.prior = 0.0f;
+            r.N = 0;
+            r.first_child = -1;
+            r.moves = legal_moves(own, opp);
+            r.meta = make_meta(0, 0xff, 0u, 0);  // a root is never terminal (MCTS_model.py:103-106)
+            store_node(N, r);
+            B[0] = make_ulonglong2(own, opp);
+        }
+        c.root = 0;
+        c.top = 1;
+        c.ply = 0;
+        c.player = player;
+        c.sims_done = 0;
+        c.pending = -1;
+        c.path_len = 0;
+        c.flags = 0;
+        c.phase = OTH_PH_RUN;
+        tile.sync();
+    }
+
+    // ---------------------------------------------------------- re-root --
+    // MCTS.make_move (MCTS_model.py:200-215): keep the chosen subtree with its
+    // statistics.  Breadth-first copy into the other arena; the destination
+    // doubles as the BFS queue.
+    __device__ void reroot(int new_root)
+    {
+        Node* Ns = N;
+        ulonglong2* Bs = B;
+        c.arena ^= 1;
+        bind_arena();
+        Node* Nd = N;
+        ulonglong2* Bd = B;
+        if (lane == 0) {
+            const Node r = load_node(Ns + new_root);
+            store_node(Nd, r);
+            Bd[0] = Bs[new_root];
+        }
+        tile.sync();
+        int top = 1, i = 0;
+        while (i < top) {
+            const int chunk = min(LANES, top - i);
+            int ofc = -1, nch = 0;
+            if (lane < chunk) {
+                const uint4 b = *(reinterpret_cast<const uint4*>(Nd + i + lane) + 1);
+                ofc = (int)b.x;
+                nch = ofc >= 0 ? (int)(b.y & 0xffu) : 0;
+            }
+            int incl = nch;
+#pragma unroll
+            for (int o = 1; o < LANES; o <<= 1) {
+                const int t = tile.shfl_up(incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int excl = incl - nch;
+            const int total = tile.shfl(incl, LANES - 1);
+            if (lane < chunk && nch > 0) Nd[i + lane].first_child = top + excl;
+            unsigned pm = tile.ballot(nch > 0);
+            while (pm) {
+                const int l = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const int o_ = tile.shfl(ofc, l), n_ = tile.shfl(nch, l), d_ = top + tile.shfl(excl, l);
+                for (int j = lane; j < n_; j += LANES) {
+                    const uint4* s = reinterpret_cast<const uint4*>(Ns + o_ + j);
+                    uint4* d = reinterpret_cast<uint4*>(Nd + d_ + j);
+                    const uint4 x0 = s[0], x1 = s[1];
+                    const ulonglong2 bb = Bs[o_ + j];
+                    d[0] = x0;
+                    d[1] = x1;
+                    Bd[d_ + j] = bb;
+                }
+            }
+            top += total;
+            i += chunk;
+            tile.sync();
+        }
+        if (lane == 0) cnt[OTH_CNT_COPIED] += top;
+        c.root = 0;
+        c.top = top;
+        c.flags &= ~2;
+    }
+
+    // ------------------------------------------------ policy target etc --
+    // Visit counts -> policy target in S.pri (MCTS_model.py:244-274).
+    __device__ void policy_target(const Node& root, double temp, double u_tie)
+    {
+        const int fc = root.first_child, nchild = meta_nchild(root.meta);
+        for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri[a] = 0.0f;
+        tile.sync();
+        for (int i = lane; i < nchild; i += LANES) {
+            const Node ch = load_node(N + fc + i);
+            S.pri[meta_action(ch.meta)] = (float)ch.N;
+        }
+        tile.sync();
+        if (fabs(temp) < 1e-1) {
+            if (lane == 0) {
+                float mx = S.pri[0];
+                for (int a = 1; a < OTH_NUM_ACTIONS; a++) mx = fmaxf(mx, S.pri[a]);
+                int nt = 0;
+                for (int a = 0; a < OTH_NUM_ACTIONS; a++) nt += (S.pri[a] == mx);
+                int k = (int)floor(u_tie * (double)nt);
+                if (k >= nt) k = nt - 1;
+                int pick = 0;
+                for (int a = 0, seen = 0; a < OTH_NUM_ACTIONS; a++)
+                    if (S.pri[a] == mx) {
+                        if (seen == k) pick = a;
+                        seen++;
+                    }
+                for (int a = 0; a < OTH_NUM_ACTIONS; a++) S.pri[a] = (a == pick) ? 1.0f : 0.0f;
+            }
+            tile.sync();
+            return;
+        }
+        if (temp != 1.0) {
+            const float ex = (float)(1.0 / temp);
+            for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri[a] = powf(S.pri[a], ex);
+            tile.sync();
+        }
+        const float norm = np_sum65_f32();
+        tile.sync();
+        if (norm < (float)1e-12) {  // all-zero counts: uniform over valid actions (:260-269)
+            const int nv = max(1, nchild);
+            for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri[a] = 0.0f;
+            tile.sync();
+            for (int i = lane; i < nchild; i += LANES) {
+                const Node ch = load_node(N + fc + i);
+                S.pri[meta_action(ch.meta)] = (float)(1.0 / (double)nv);
+            }
+        } else {
+            for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri[a] = __fdiv_rn(S.pri[a], norm);
+        }
+        tile.sync();
+    }
+
+    // np.random.choice(65, p) given its uniform (self_play_worker.py:75)
+    __device__ int sample_action(double u)
+    {
+        int act = 0;
+        if (lane == 0) {
+            double last = 0.0;
+            for (int a = 0; a < OTH_NUM_ACTIONS; a++) last = __dadd_rn(last, (double)S.pri[a]);
+            double acc = 0.0;
+            for (int a = 0; a < OTH_NUM_ACTIONS; a++) {
+                acc = __dadd_rn(acc, (double)S.pri[a]);
+                if (__ddiv_rn(acc, last) <= u) act = a + 1;
+            }
+        }
+        return tile.shfl(act, 0);
+    }
+
+    __device__ double uniform_for(uint32_t purpose, int ply)
+    {
+        const Philox4 r = philox4x32_10(P.cfg.seed, (uint64_t)c.game_id, (uint32_t)ply, purpose);
+        return u01_53(r.x, r.y);
+    }
+
+    // get_training_data (self_play_worker.py:8-35) + hand-off of the game's
+    // replay tuples to the output ring.
+    __device__ void emit_game(int nply, int winner)
+    {
+        long long base = 0, gi = 0;
+        if (lane == 0) {
+            base = (long long)atomicAdd(P.counters + OTH_CNT_POSITIONS, (unsigned long long)nply);
+            gi = (long long)atomicAdd(P.counters + OTH_CNT_OUT_GAMES, 1ULL);
+        }
+        base = tile.shfl(base, 0);
+        gi = tile.shfl(gi, 0);
+        if (base + nply > P.cfg.out_pos_cap || gi >= P.cfg.out_game_cap) {
+            fail(OTH_ERR_OUT_OVERFLOW);
+            return;
+        }
+        const size_t tb = (size_t)slot * OTH_MAX_PLIES;
+        if (lane == 0) {
+            const double lam = P.cfg.lambda;
+            double g_next = 0.0;
+            int next_player = 0;
+            for (int t = nply - 1; t >= 0; t--) {
+                const int pl = (int)(int8_t)(P.traj_meta[tb + t] & 0xff);
+                const double mc = winner == 0 ? 0.0 : (pl == winner ? 1.0 : -1.0);
+                double g;
+                if (t == nply - 1) g = mc;
+                else {
+                    const double sign = pl == next_player ? 1.0 : -1.0;
+                    const double a = __dmul_rn(1.0 - lam, P.traj_rootv[tb + t]);
+                    const double b = __dmul_rn(__dmul_rn(lam, sign), g_next);
+                    g = __dadd_rn(a, b);
+                }
+                P.out_value[base + t] = g;
+                g_next = g;
+                next_player = pl;
+            }
+            long long* gd = P.out_games + gi * 4;
+            gd[0] = c.game_id;
+            gd[1] = base;
+            gd[2] = nply;
+            gd[3] = winner;
+        }
+        for (int t = lane; t < nply; t += LANES) {
+            P.out_board[base + t] = P.traj_board[tb + t];
+            const int m = P.traj_meta[tb + t];
+            P.out_meta[base + t] = (c.game_id << 16) | ((long long)t << 8) | (long long)(m & 0xff);
+        }
+        const float* sp = P.traj_pi + tb * OTH_NUM_ACTIONS;
+        float* dp = P.out_pi + (size_t)base * OTH_NUM_ACTIONS;
+        for (int e = lane; e < nply * OTH_NUM_ACTIONS; e += LANES) dp[e] = sp[e];
+        if (lane == 0) cnt[OTH_CNT_GAMES] += 1;
+    }
+
+    // One self-play ply after its search (self_play_worker.py:64-88).
+    __device__ void finish_move()
+    {
+        const Node root = load_node(N + c.root);
+        const int T = c.ply;
+        if (T >= OTH_MAX_PLIES) {
+            fail(OTH_ERR_PLY_OVERFLOW);
+            return;
+        }
+        const size_t tb = (size_t)slot * OTH_MAX_PLIES;
+        const double temp = T < P.cfg.num_exploratory_moves ? P.cfg.temperature : 0.0;
+        double ut = 0.0, um = 0.0;
+        if (P.cfg.inject_random) {
+            ut = P.u_tie[tb + T];
+            um = P.u_move[tb + T];
+        } else {
+            ut = uniform_for(kPurposeTie, T);
+            um = uniform_for(kPurposeMove, T);
+            if (lane == 0) {
+                P.u_tie[tb + T] = ut;
+                P.u_move[tb + T] = um;
+            }
+        }
+        policy_target(root, temp, ut);
+        for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) P.traj_pi[(tb + T) * OTH_NUM_ACTIONS + a] = S.pri[a];
+        const int action = sample_action(um);
+        if (lane == 0) {
+            P.traj_board[tb + T] = B[c.root];
+            P.traj_rootv[tb + T] = root.N ? __ddiv_rn(root.W, (double)root.N) : 0.0;  // mcts.root.value, :72-73
+            P.traj_meta[tb + T] = (c.player & 0xff) | (action << 8);
+            cnt[OTH_CNT_MOVES] += 1;
+        }
+        // mcts.make_move(action): locate the child (KeyError if absent)
+        const int fc = root.first_child, nchild = meta_nchild(root.meta);
+        int ci = -1;
+        uint32_t cmeta = 0;
+        for (int i = lane; i < nchild; i += LANES) {
+            const uint4 b = *(reinterpret_cast<const uint4*>(N + fc + i) + 1);
+            if (meta_action(b.y) == action) {
+                ci = i;
+                cmeta = b.y;
+            }
+        }
+        const unsigned hit = tile.ballot(ci >= 0);
+        if (!hit) {
+            fail(OTH_ERR_BAD_ACTION);
+            return;
+        }
+        const int src = __ffs(hit) - 1;
+        ci = tile.shfl(ci, src);
+        cmeta = tile.shfl(cmeta, src);
+        tile.sync();
+        if (meta_flags(cmeta) & kFlagTerminal) {
+            // reward is read from the mover's side (:78-82); the child's terminal value is the opponent's
+            const int reward = -meta_tvalue(cmeta);
+            const int winner = reward > 0 ? c.player : (reward < 0 ? -c.player : 0);
+            emit_game(T + 1, winner);
+            if (c.phase == OTH_PH_ERROR) return;
+            if (c.games_left > 0) c.games_left--;
+            if (c.games_left == 0) {
+                c.phase = OTH_PH_DONE;
+                return;
+            }
+            c.game_id += (long long)P.cfg.game_id_stride;
+            init_tree(INIT_BLACK, INIT_WHITE, 1);
+            return;
+        }
+        reroot(fc + ci);
+        c.ply = T + 1;
+        c.player = -c.player;
+        c.sims_done = 0;
+    }
+
+    // ------------------------------------------------------ slot driver --
+    __device__ void run_slot()
+    {
+        c = P.ctl[slot];
+        bind_arena();
+        const bool stub = P.cfg.eval_kind != OTH_EVAL_EXTERNAL;
+        if (c.phase == OTH_PH_WAIT_EVAL) {
+            // network outputs for the pending leaf are in priors/values[slot]
+            const float* pr = P.priors + (size_t)slot * OTH_NUM_ACTIONS;
+            for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri[a] = pr[a];
+            const int* gp = P.path + (size_t)slot * P.cfg.path_cap;
+            for (int d = lane; d < c.path_len; d += LANES) S.path[d] = gp[d];
+            const double value = (double)P.values[slot];
+            tile.sync();
+            const bool root_init = c.flags & 1;
+            if (expand(c.pending, root_init)) {
+                backup(c.path_len, value);
+                if (!root_init) {
+                    c.sims_done++;
+                    if (lane == 0) cnt[OTH_CNT_SIMS] += 1;
+                }
+                if (lane == 0) {
+                    cnt[OTH_CNT_EVALS] += 1;
+                    if ((unsigned long long)c.path_len > cnt[OTH_CNT_MAX_DEPTH]) cnt[OTH_CNT_MAX_DEPTH] = c.path_len;
+                }
+                c.flags &= ~1;
+                c.pending = -1;
+                c.phase = OTH_PH_RUN;
+            }
+        }
+        int budget = P.cfg.max_inline_sims;
+        while (c.phase == OTH_PH_RUN && budget > 0) {
+            if (c.sims_done >= P.cfg.num_simulations) {
+                if (!P.cfg.self_play) {
+                    c.phase = OTH_PH_IDLE;
+                    break;
+                }
+                finish_move();
+                budget--;
+                continue;
+            }
+            int leaf, depth;
+            Node nd;
+            const int r = descend(leaf, depth, nd);
+            if (r < 0) break;
+            if (r == 1) {  // terminal node: back up its value again, no evaluation (:381-384)
+                backup(depth, (double)meta_tvalue(nd.meta));
+                c.sims_done++;
+                budget--;
+                if (lane == 0) {
+                    cnt[OTH_CNT_SIMS] += 1;
+                    cnt[OTH_CNT_TERMINAL] += 1;
+                }
+                continue;
+            }
+            const bool root_init = (depth == 1);  // the leaf is the root: policy_improve_step :234-235
+            const ulonglong2 lb = B[leaf];
+            if (stub) {
+                const double value = eval_stub(lb.x, lb.y);
+                if (!expand(leaf, root_init)) break;
+                backup(depth, value);
+                if (!root_init) {
+                    c.sims_done++;
+                    if (lane == 0) cnt[OTH_CNT_SIMS] += 1;
+                }
+                if (lane == 0) {
+                    cnt[OTH_CNT_EVALS] += 1;
+                    if ((unsigned long long)depth > cnt[OTH_CNT_MAX_DEPTH]) cnt[OTH_CNT_MAX_DEPTH] = depth;
+                }
+                budget--;
+                continue;
+            }
+            c.pending = leaf;
+            c.path_len = depth;
+            c.flags = (c.flags & ~1) | (root_init ? 1 : 0);
+            c.phase = OTH_PH_WAIT_EVAL;
+            write_nn_input(lb.x, lb.y);
+            tile.sync();
+            int* gp = P.path + (size_t)slot * P.cfg.path_cap;
+            for (int d = lane; d < depth; d += LANES) gp[d] = S.path[d];
+        }
+        if (lane == 0) {
+            if (c.phase == OTH_PH_ERROR) cnt[OTH_CNT_ERRORS] += 1;
+            if (c.phase == OTH_PH_WAIT_EVAL) cnt[OTH_CNT_WAITING] += 1;
+            if (c.phase == OTH_PH_WAIT_EVAL || c.phase == OTH_PH_RUN) cnt[OTH_CNT_ACTIVE] += 1;
+            if ((unsigned long long)c.top > cnt[OTH_CNT_MAX_TOP]) cnt[OTH_CNT_MAX_TOP] = c.top;
+            P.ctl[slot] = c;
+        }
+        tile.sync();
+    }
+};
+
+__device__ __forceinline__ void flush_counters(unsigned long long* blk, const unsigned long long* cnt, unsigned long long* global,
+                                               bool leader)
+{
+    // block-level reduction in shared memory, then one global atomic per counter per block
+    if (leader) {
+#pragma unroll
+        for (int i = 0; i < CNT_LOCAL; i++) {
+            if (cnt[i] == 0) continue;
+            if (i == OTH_CNT_MAX_TOP || i == OTH_CNT_MAX_DEPTH) atomicMax(blk + i, cnt[i]);
+            else atomicAdd(blk + i, cnt[i]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < CNT_LOCAL && blk[threadIdx.x]) {
+        const int i = threadIdx.x;
+        if (i == OTH_CNT_POSITIONS || i == OTH_CNT_OUT_GAMES) return;  // bumped directly by emit_game
+        if (i == OTH_CNT_MAX_TOP || i == OTH_CNT_MAX_DEPTH) atomicMax(global + i, blk[i]);
+        else atomicAdd(global + i, blk[i]);
+    }
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(kBlock) k_mcts_step(const Params P)
+{
+    __shared__ Scratch scratch[kBlock / LANES];
+    __shared__ unsigned long long blk_cnt[CNT_LOCAL];
+    if (threadIdx.x < CNT_LOCAL) blk_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
+    Ctx<LANES> ctx(tile, P, scratch[threadIdx.x / LANES]);
+    const int groups = (gridDim.x * kBlock) / LANES;
+    for (int s = (blockIdx.x * kBlock + threadIdx.x) / LANES; s < P.cfg.n_slots; s += groups) {
+        ctx.slot = s;
+        ctx.run_slot();
+    }
+    flush_counters(blk_cnt, ctx.cnt, P.counters, ctx.lane == 0);
+}
+
+// Start fresh games (self-play) on every slot.
+template <int LANES>
+__global__ void __launch_bounds__(kBlock) k_mcts_reset(const Params P)
+{
+    __shared__ Scratch scratch[kBlock / LANES];
+    cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
+    Ctx<LANES> ctx(tile, P, scratch[threadIdx.x / LANES]);
+    const int groups = (gridDim.x * kBlock) / LANES;
+    for (int s = (blockIdx.x * kBlock + threadIdx.x) / LANES; s < P.cfg.n_slots; s += groups) {
+        ctx.slot = s;
+        oth_mcts_ctl z = {};
+        ctx.c = z;
+        ctx.c.game_id = (long long)(P.cfg.game_id_base + (uint64_t)s);
+        ctx.c.games_left = P.cfg.games_per_slot < 0 ? -1 : P.cfg.games_per_slot;
+        ctx.init_tree(INIT_BLACK, INIT_WHITE, 1);
+        if (P.cfg.games_per_slot == 0) ctx.c.phase = OTH_PH_DONE;
+        if (ctx.lane == 0) P.ctl[s] = ctx.c;
+    }
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(kBlock) k_mcts_set_roots(const Params P, const u64* own, const u64* opp, const int8_t* players)
+{
+    __shared__ Scratch scratch[kBlock / LANES];
+    cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
+    Ctx<LANES> ctx(tile, P, scratch[threadIdx.x / LANES]);
+    const int groups = (gridDim.x * kBlock) / LANES;
+    for (int s = (blockIdx.x * kBlock + threadIdx.x) / LANES; s < P.cfg.n_slots; s += groups) {
+        ctx.slot = s;
+        oth_mcts_ctl z = {};
+        ctx.c = z;
+        ctx.c.game_id = (long long)(P.cfg.game_id_base + (uint64_t)s);
+        ctx.c.games_left = -1;
+        ctx.init_tree(own[s], opp[s], players[s]);
+        ctx.c.phase = OTH_PH_IDLE;
+        if (ctx.lane == 0) P.ctl[s] = ctx.c;
+    }
+}
+
+__global__ void k_mcts_begin_search(const Params P)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.cfg.n_slots) return;
+    oth_mcts_ctl* c = P.ctl + s;
+    if (c->phase == OTH_PH_IDLE) {
+        c->sims_done = 0;
+        c->phase = OTH_PH_RUN;
+    }
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(kBlock) k_mcts_advance(const Params P, const int32_t* actions)
+{
+    __shared__ Scratch scratch[kBlock / LANES];
+    __shared__ unsigned long long blk_cnt[CNT_LOCAL];
+    if (threadIdx.x < CNT_LOCAL) blk_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
+    Ctx<LANES> ctx(tile, P, scratch[threadIdx.x / LANES]);
+    const int groups = (gridDim.x * kBlock) / LANES;
+    for (int s = (blockIdx.x * kBlock + threadIdx.x) / LANES; s < P.cfg.n_slots; s += groups) {
+        const int action = actions[s];
+        if (action < 0) continue;
+        ctx.slot = s;
+        ctx.c = P.ctl[s];
+        if (ctx.c.phase == OTH_PH_ERROR) continue;
+        ctx.bind_arena();
+        const Node root = load_node(ctx.N + ctx.c.root);
+        const int fc = root.first_child, nchild = root.first_child < 0 ? 0 : meta_nchild(root.meta);
+        int ci = -1;
+        for (int i = ctx.lane; i < nchild; i += LANES) {
+            const uint4 b = *(reinterpret_cast<const uint4*>(ctx.N + fc + i) + 1);
+            if (meta_action(b.y) == action) ci = i;
+        }
+        const unsigned hit = tile.ballot(ci >= 0);
+        if (!hit) {
+            ctx.c.error |= OTH_ERR_BAD_ACTION;  // KeyError; the tree is left as it was
+        } else {
+            ci = tile.shfl(ci, __ffs(hit) - 1);
+            ctx.reroot(fc + ci);
+            ctx.c.ply += 1;
+            ctx.c.player = -ctx.c.player;
+            ctx.c.sims_done = 0;
+            ctx.c.phase = OTH_PH_IDLE;
+        }
+        if (ctx.lane == 0) P.ctl[s] = ctx.c;
+        tile.sync();
+    }
+    flush_counters(blk_cnt, ctx.cnt, P.counters, ctx.lane == 0);
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(kBlock) k_mcts_root_stats(const Params P, int32_t* counts, double* child_value, double* child_prior,
+                                                            double* root_value, int32_t* root_n, u64* root_board)
+{
+    cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
+    const int lane = tile.thread_rank();
+    const int groups = (gridDim.x * kBlock) / LANES;
+    for (int s = (blockIdx.x * kBlock + threadIdx.x) / LANES; s < P.cfg.n_slots; s += groups) {
+        const oth_mcts_ctl c = P.ctl[s];
+        const size_t base = ((size_t)s * 2 + (size_t)c.arena) * (size_t)P.cfg.node_cap;
+        const Node* N = P.nodes + base;
+        const Node root = load_node(N + c.root);
+        for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) {
+            if (counts) counts[(size_t)s * OTH_NUM_ACTIONS + a] = 0;
+            if (child_value) child_value[(size_t)s * OTH_NUM_ACTIONS + a] = 0.0;
+            if (child_prior) child_prior[(size_t)s * OTH_NUM_ACTIONS + a] = 0.0;
+        }
+        tile.sync();
+        const int nchild = root.first_child < 0 ? 0 : meta_nchild(root.meta);
+        for (int i = lane; i < nchild; i += LANES) {
+            const Node ch = load_node(N + root.first_child + i);
+            const int a = meta_action(ch.meta);
+            if (counts) counts[(size_t)s * OTH_NUM_ACTIONS + a] = ch.N;
+            if (child_value) child_value[(size_t)s * OTH_NUM_ACTIONS + a] = ch.N ? ch.W / (double)ch.N : 0.0;
+            if (child_prior)
+                child_prior[(size_t)s * OTH_NUM_ACTIONS + a] =
+                    (c.flags & 2) ? P.root_prior64[(size_t)s * OTH_MAX_CHILDREN + i] : (double)ch.prior;
+        }
+        if (lane == 0) {
+            if (root_value) root_value[s] = root.N ? root.W / (double)root.N : 0.0;
+            if (root_n) root_n[s] = root.N;
+            if (root_board) {
+                const ulonglong2 b = P.boards[base + c.root];
+                root_board[2 * (size_t)s] = b.x;
+                root_board[2 * (size_t)s + 1] = b.y;
+            }
+        }
+    }
+}
+
+int check_cfg(const oth_mcts_config* cfg)
+{
+    if (!cfg) return OTH_E_ARG;
+    if (cfg->n_slots <= 0 || cfg->node_cap < 64 || cfg->path_cap < 2 || cfg->path_cap > 256) return OTH_E_ARG;
+    if (cfg->num_simulations < 0 || cfg->max_inline_sims <= 0) return OTH_E_ARG;
+    if (cfg->lanes != 8 && cfg->lanes != 16 && cfg->lanes != 32) return OTH_E_ARG;
+    if (cfg->eval_kind < OTH_EVAL_EXTERNAL || cfg->eval_kind > OTH_EVAL_STUB_H) return OTH_E_ARG;
+    if (cfg->fused_softmax) return OTH_E_ARG;  // reserved
+    if (cfg->self_play && (cfg->out_pos_cap <= 0 || cfg->out_game_cap <= 0)) return OTH_E_ARG;
+    return OTH_OK;
+}
+
+int make_params(const oth_mcts_config* cfg, const oth_mcts_buffers* b, Params* p)
+{
+    const int rc = check_cfg(cfg);
+    if (rc != OTH_OK) return rc;
+    if (!b) return OTH_E_ARG;
+    for (int i = 0; i < OTH_BUF_COUNT; i++) {
+        const bool out_buf = i >= OTH_BUF_OUT_BOARD && i <= OTH_BUF_OUT_GAMES;
+        const bool traj_buf = i >= OTH_BUF_TRAJ_BOARD && i <= OTH_BUF_TRAJ_META;
+        if (!b->buf[i] && !((out_buf || traj_buf) && !cfg->self_play)) return OTH_E_ARG;
+    }
+    p->cfg = *cfg;
+    p->nodes = (Node*)b->buf[OTH_BUF_NODES];
+    p->boards = (ulonglong2*)b->buf[OTH_BUF_BOARDS];
+    p->ctl = (oth_mcts_ctl*)b->buf[OTH_BUF_CTL];
+    p->path = (int*)b->buf[OTH_BUF_PATH];
+    p->root_prior64 = (double*)b->buf[OTH_BUF_ROOT_PRIOR64];
+    p->noise = (double*)b->buf[OTH_BUF_NOISE];
+    p->u_move = (double*)b->buf[OTH_BUF_U_MOVE];
+    p->u_tie = (double*)b->buf[OTH_BUF_U_TIE];
+    p->traj_board = (ulonglong2*)b->buf[OTH_BUF_TRAJ_BOARD];
+    p->traj_pi = (float*)b->buf[OTH_BUF_TRAJ_PI];
+    p->traj_rootv = (double*)b->buf[OTH_BUF_TRAJ_ROOTV];
+    p->traj_meta = (int*)b->buf[OTH_BUF_TRAJ_META];
+    p->out_board = (ulonglong2*)b->buf[OTH_BUF_OUT_BOARD];
+    p->out_pi = (float*)b->buf[OTH_BUF_OUT_PI];
+    p->out_value = (double*)b->buf[OTH_BUF_OUT_VALUE];
+    p->out_meta = (long long*)b->buf[OTH_BUF_OUT_META];
+    p->out_games = (long long*)b->buf[OTH_BUF_OUT_GAMES];
+    p->counters = (unsigned long long*)b->buf[OTH_BUF_COUNTERS];
+    p->priors = nullptr;
+    p->values = nullptr;
+    p->nn_input = nullptr;
+    p->c_puct_f32 = (float)cfg->c_puct;
+    return OTH_OK;
+}
+
+// Persistent-style grid: whole SMs' worth of blocks, groups stride over the slots.
+int mcts_grid(const oth_mcts_config* cfg)
+{
+    const int64_t need = ((int64_t)cfg->n_slots * cfg->lanes + kBlock - 1) / kBlock;
+    const int64_t full = (int64_t)sm_count() * 16;  // 16 blocks of 128 threads fill an SM
+    return (int)(need < full ? need : full);
+}
+
+#define LAUNCH_LANES(kernel, grid, stream, ...)                                              \
+    do {                                                                                     \
+        if (cfg->lanes == 32) kernel<32><<<grid, kBlock, 0, (cudaStream_t)stream>>>(__VA_ARGS__); \
+        else if (cfg->lanes == 16) kernel<16><<<grid, kBlock, 0, (cudaStream_t)stream>>>(__VA_ARGS__); \
+        else kernel<8><<<grid, kBlock, 0, (cudaStream_t)stream>>>(__VA_ARGS__);                \
+    } while (0)
+
+}  // namespace
+
+extern "C" int oth_mcts_buffer_bytes(const oth_mcts_config* cfg, int64_t* out)
+{
+    const int rc = check_cfg(cfg);
+    if (rc != OTH_OK) return rc;
+    if (!out) return OTH_E_ARG;
+    const int64_t G = cfg->n_slots, cap = cfg->node_cap, T = OTH_MAX_PLIES;
+    const bool sp = cfg->self_play != 0;
+    out[OTH_BUF_NODES] = G * 2 * cap * 32;
+    out[OTH_BUF_BOARDS] = G * 2 * cap * 16;
+    out[OTH_BUF_CTL] = G * (int64_t)sizeof(oth_mcts_ctl);
+    out[OTH_BUF_PATH] = G * cfg->path_cap * 4;
+    out[OTH_BUF_ROOT_PRIOR64] = G * OTH_MAX_CHILDREN * 8;
+    out[OTH_BUF_NOISE] = G * OTH_NUM_ACTIONS * 8;
+    out[OTH_BUF_U_MOVE] = G * T * 8;
+    out[OTH_BUF_U_TIE] = G * T * 8;
+    out[OTH_BUF_TRAJ_BOARD] = sp ? G * T * 16 : 0;
+    out[OTH_BUF_TRAJ_PI] = sp ? G * T * OTH_NUM_ACTIONS * 4 : 0;
+    out[OTH_BUF_TRAJ_ROOTV] = sp ? G * T * 8 : 0;
+    out[OTH_BUF_TRAJ_META] = sp ? G * T * 4 : 0;
+    out[OTH_BUF_OUT_BOARD] = sp ? cfg->out_pos_cap * 16 : 0;
+    out[OTH_BUF_OUT_PI] = sp ? cfg->out_pos_cap * OTH_NUM_ACTIONS * 4 : 0;
+    out[OTH_BUF_OUT_VALUE] = sp ? cfg->out_pos_cap * 8 : 0;
+    out[OTH_BUF_OUT_META] = sp ? cfg->out_pos_cap * 8 : 0;
+    out[OTH_BUF_OUT_GAMES] = sp ? cfg->out_game_cap * 32 : 0;
+    out[OTH_BUF_COUNTERS] = 16 * 8;
+    return OTH_OK;
+}
+
+extern "C" int oth_mcts_reset(const oth_mcts_config* cfg, const oth_mcts_buffers* b, void* stream)
+{
+    Params p;
+    const int rc = make_params(cfg, b, &p);
+    if (rc != OTH_OK) return rc;
+    int e = cuda_status(cudaMemsetAsync(p.counters, 0, 16 * 8, (cudaStream_t)stream));
+    if (e != OTH_OK) return e;
+    LAUNCH_LANES(k_mcts_reset, mcts_grid(cfg), stream, p);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int oth_mcts_set_roots(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const uint64_t* own, const uint64_t* opp,
+                                  const int8_t* players, void* stream)
+{
+    Params p;
+    const int rc = make_params(cfg, b, &p);
+    if (rc != OTH_OK) return rc;
+    if (!own || !opp || !players) return OTH_E_ARG;
+    int e = cuda_status(cudaMemsetAsync(p.counters, 0, 16 * 8, (cudaStream_t)stream));
+    if (e != OTH_OK) return e;
+    LAUNCH_LANES(k_mcts_set_roots, mcts_grid(cfg), stream, p, (const u64*)own, (const u64*)opp, players);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int oth_mcts_begin_search(const oth_mcts_config* cfg, const oth_mcts_buffers* b, void* stream)
+{
+    Params p;
+    const int rc = make_params(cfg, b, &p);
+    if (rc != OTH_OK) return rc;
+    k_mcts_begin_search<<<(cfg->n_slots + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const float* priors, const float* values,
+                             float* nn_input, void* stream)
+{
+    Params p;
+    const int rc = make_params(cfg, b, &p);
+    if (rc != OTH_OK) return rc;
+    if (cfg->eval_kind == OTH_EVAL_EXTERNAL && (!priors || !values || !nn_input)) return OTH_E_ARG;
+    p.priors = priors;
+    p.values = values;
+    p.nn_input = nn_input;
+    // per-launch gauges
+    int e = cuda_status(cudaMemsetAsync(p.counters + OTH_CNT_WAITING, 0, 2 * 8, (cudaStream_t)stream));
+    if (e != OTH_OK) return e;
+    LAUNCH_LANES(k_mcts_step, mcts_grid(cfg), stream, p);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int oth_mcts_advance(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const int32_t* actions, void* stream)
+{
+    Params p;
+    const int rc = make_params(cfg, b, &p);
+    if (rc != OTH_OK) return rc;
+    if (!actions) return OTH_E_ARG;
+    LAUNCH_LANES(k_mcts_advance, mcts_grid(cfg), stream, p, actions);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int oth_mcts_root_stats(const oth_mcts_config* cfg, const oth_mcts_buffers* b, int32_t* counts, double* child_value,
+                                   double* child_prior, double* root_value, int32_t* root_n, uint64_t* root_board, void* stream)
+{
+    Params p;
+    const int rc = make_params(cfg, b, &p);
+    if (rc != OTH_OK) return rc;
+    LAUNCH_LANES(k_mcts_root_stats, mcts_grid(cfg), stream, p, counts, child_value, child_prior, root_value, root_n, (u64*)root_board);
+    return cuda_status(cudaGetLastError());
+}

@@ -1,0 +1,284 @@
+"""Host driver of the batched MCTS self-play engine (CUDA kernels in csrc/mcts_kernels.cu).
+
+PyTorch is used for device memory, streams, CUDA graphs and the policy/value
+network only; every search / env / self-play step is a kernel behind the C ABI
+(include/othello_b200.h).  One process drives one GPU; games are sharded over
+ranks by game id (no collective on the search path).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def default_node_cap(num_simulations):
+    """Arena size per slot: kept subtree + one expansion (<= 33 children) per simulation,
+    with headroom; measured maxima are ~6.3k slots at 400 simulations."""
+    return int(max(2048, 40 * num_simulations + 1024))
+
+
+class MctsEngine:
+    """Owns the device buffers of ``n_slots`` concurrent search trees and launches the kernels.
+
+    ``args`` carries the reference's keys (train.py:399-425): c_puct, num_simulations,
+    dirichlet_alpha, dirichlet_epsilon, mcts_temperature, num_exploratory_moves, lambda.
+    """
+
+    def __init__(self, n_slots, args, *, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=-1,
+                 device="cuda:0", node_cap=None, path_cap=128, max_inline_sims=8, inject_random=False, lanes=32,
+                 seed=0, game_id_base=0, game_id_stride=None, stub_salt=0, out_pos_cap=None, out_game_cap=None):
+        _lib.require_device()
+        self.device = torch.device(device)
+        self.n_slots = int(n_slots)
+        cfg = _lib.MctsConfig()
+        cfg.n_slots = self.n_slots
+        cfg.num_simulations = int(args["num_simulations"])
+        cfg.node_cap = int(node_cap or default_node_cap(cfg.num_simulations))
+        cfg.path_cap = int(path_cap)
+        cfg.num_exploratory_moves = int(args.get("num_exploratory_moves", 0))
+        cfg.eval_kind = int(eval_kind)
+        cfg.self_play = 1 if self_play else 0
+        cfg.games_per_slot = int(games_per_slot)
+        cfg.max_inline_sims = int(max_inline_sims)
+        cfg.inject_random = 1 if inject_random else 0
+        cfg.fused_softmax = 0
+        cfg.lanes = int(lanes)
+        if out_game_cap is None:
+            out_game_cap = self.n_slots * (2 if games_per_slot < 0 else max(1, games_per_slot)) + 16
+        if out_pos_cap is None:
+            out_pos_cap = out_game_cap * 72
+        cfg.out_pos_cap = int(out_pos_cap)
+        cfg.out_game_cap = int(out_game_cap)
+        cfg.c_puct = float(args["c_puct"])
+        cfg.dirichlet_alpha = float(args.get("dirichlet_alpha", 0.03))
+        cfg.dirichlet_epsilon = float(args.get("dirichlet_epsilon", 0.0))
+        cfg.temperature = float(args.get("mcts_temperature", 1.0))
+        cfg.lambda_ = float(args.get("lambda", 1.0))
+        cfg.seed = int(seed)
+        cfg.game_id_base = int(game_id_base)
+        cfg.game_id_stride = int(game_id_stride if game_id_stride is not None else self.n_slots)
+        cfg.stub_salt = int(stub_salt)
+        self.cfg = cfg
+        self.L = _lib.lib()
+        sizes = (C.c_int64 * _lib.BUF_COUNT)()
+        _lib.check(self.L.oth_mcts_buffer_bytes(C.byref(cfg), sizes), "oth_mcts_buffer_bytes")
+        self.buf_bytes = list(sizes)
+        self.bufs = _lib.MctsBuffers()
+        self._t = []
+        with torch.cuda.device(self.device):
+            for i, nb in enumerate(self.buf_bytes):
+                # int64 storage: every buffer is at least 8-byte aligned (torch gives 512 B)
+                t = torch.zeros((max(nb, 8) + 7) // 8, dtype=torch.int64, device=self.device)
+                self._t.append(t)
+                self.bufs.buf[i] = t.data_ptr()
+            self.nn_input = torch.zeros((self.n_slots, 1, 8, 8), dtype=torch.float32, device=self.device)
+            self.priors = torch.zeros((self.n_slots, 65), dtype=torch.float32, device=self.device)
+            self.values = torch.zeros((self.n_slots,), dtype=torch.float32, device=self.device)
+        self.launches = 0
+
+    # ---------------------------------------------------------------- views
+    def _view(self, i, dtype, shape):
+        return self._t[i].view(dtype)[: int(np.prod(shape))].view(*shape)
+
+    @property
+    def counters_t(self):
+        return self._t[_lib.BUF_COUNTERS][:16]
+
+    def counters(self):
+        v = self.counters_t.cpu().numpy()
+        return {n: int(v[i]) for i, n in enumerate(_lib.CNT_NAMES)}
+
+    def ctl(self):
+        raw = self._t[_lib.BUF_CTL][: self.n_slots * 8].cpu().numpy().view(np.int32).reshape(self.n_slots, 16)
+        names = ["phase", "root", "top", "arena", "ply", "sims_done", "pending", "path_len", "flags", "player", "games_left",
+                 "error"]
+        d = {n: raw[:, i].copy() for i, n in enumerate(names)}
+        d["game_id"] = raw[:, 12:14].copy().view(np.int64).reshape(-1)
+        return d
+
+    @property
+    def noise(self):
+        return self._view(_lib.BUF_NOISE, torch.float64, (self.n_slots, 65))
+
+    @property
+    def u_move(self):
+        return self._view(_lib.BUF_U_MOVE, torch.float64, (self.n_slots, _lib.OTH_MAX_PLIES))
+
+    @property
+    def u_tie(self):
+        return self._view(_lib.BUF_U_TIE, torch.float64, (self.n_slots, _lib.OTH_MAX_PLIES))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _call(self, fn, *a):
+        with torch.cuda.device(self.device):
+            _lib.check(fn(C.byref(self.cfg), C.byref(self.bufs), *a), fn.__name__)
+
+    # -------------------------------------------------------------- kernels
+    def reset(self):
+        self._call(self.L.oth_mcts_reset, self._stream())
+
+    def set_roots(self, own, opp, players):
+        """own/opp int64 [n_slots] device tensors, players int8 [n_slots]."""
+        self._call(self.L.oth_mcts_set_roots, own.data_ptr(), opp.data_ptr(), players.data_ptr(), self._stream())
+
+    def begin_search(self):
+        self._call(self.L.oth_mcts_begin_search, self._stream())
+
+    def step(self):
+        """One launch of the fused expand/backup/select/self-play kernel on the engine's
+        priors/values/nn_input tensors."""
+        self._call(self.L.oth_mcts_step, self.priors.data_ptr(), self.values.data_ptr(), self.nn_input.data_ptr(),
+                   self._stream())
+        self.launches += 1
+
+    def advance(self, actions):
+        self._call(self.L.oth_mcts_advance, actions.data_ptr(), self._stream())
+
+    def root_stats(self):
+        n = self.n_slots
+        dev = self.device
+        counts = torch.empty((n, 65), dtype=torch.int32, device=dev)
+        cval = torch.empty((n, 65), dtype=torch.float64, device=dev)
+        cpri = torch.empty((n, 65), dtype=torch.float64, device=dev)
+        rv = torch.empty(n, dtype=torch.float64, device=dev)
+        rn = torch.empty(n, dtype=torch.int32, device=dev)
+        rb = torch.empty((n, 2), dtype=torch.int64, device=dev)
+        self._call(self.L.oth_mcts_root_stats, counts.data_ptr(), cval.data_ptr(), cpri.data_ptr(), rv.data_ptr(),
+                   rn.data_ptr(), rb.data_ptr(), self._stream())
+        return dict(counts=counts, child_value=cval, child_prior=cpri, root_value=rv, root_n=rn, root_board=rb)
+
+    def raise_on_error(self):
+        c = self.ctl()
+        bad = np.nonzero(c["error"])[0]
+        if len(bad):
+            e = int(c["error"][bad[0]])
+            names = [v for k, v in _lib.ERR_NAMES.items() if e & k]
+            if e == 16:
+                raise KeyError("; ".join(names))
+            raise _lib.OthelloB200Error(f"slot {int(bad[0])}: {'; '.join(names)} (node_cap={self.cfg.node_cap})")
+
+    # -------------------------------------------------------------- outputs
+    def drain(self, to_host=True):
+        """Collect the replay tuples of games finished since the last drain and reset the
+        output ring.  Returns dict(boards int64[n,2] (own,opp canonical), pis f32[n,65],
+        values f64[n], meta int64[n], games int64[g,4] = (game_id, first, n, winner))."""
+        cnt = self.counters_t[_lib.CNT_POSITIONS:_lib.CNT_OUT_GAMES + 1].cpu()
+        n, g = int(cnt[0]), int(cnt[1])
+        n, g = min(n, self.cfg.out_pos_cap), min(g, self.cfg.out_game_cap)
+        out = dict(
+            boards=self._view(_lib.BUF_OUT_BOARD, torch.int64, (self.cfg.out_pos_cap, 2))[:n],
+            pis=self._view(_lib.BUF_OUT_PI, torch.float32, (self.cfg.out_pos_cap, 65))[:n],
+            values=self._view(_lib.BUF_OUT_VALUE, torch.float64, (self.cfg.out_pos_cap,))[:n],
+            meta=self._view(_lib.BUF_OUT_META, torch.int64, (self.cfg.out_pos_cap,))[:n],
+            games=self._view(_lib.BUF_OUT_GAMES, torch.int64, (self.cfg.out_game_cap, 4))[:g],
+        )
+        states = torch.empty((n, 8, 8), dtype=torch.int8, device=self.device)
+        if n:
+            with torch.cuda.device(self.device):
+                _lib.check(self.L.oth_unpack_canonical(out["boards"].data_ptr(), states.data_ptr(), n, self._stream()))
+        out["states"] = states
+        if to_host:
+            out = {k: v.cpu() for k, v in out.items()}
+        else:
+            out = {k: v.clone() for k, v in out.items()}
+        self.counters_t[_lib.CNT_POSITIONS:_lib.CNT_OUT_GAMES + 1].zero_()
+        return out
+
+
+class BatchedPolicy:
+    """The policy/value network at the engine boundary.  It stays PyTorch
+    (Models.py:93-221 architectures): ``policy(x[B,1,8,8]) -> (logits[B,65], value[B,1])``,
+    softmax over actions as Models.py:24-25.  Runs in eval mode on the GPU; ``dtype``
+    torch.bfloat16 uses autocast + channels_last."""
+
+    def __init__(self, policy, device="cuda:0", dtype=torch.float32):
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.policy = policy.to(self.device).eval()
+        if dtype != torch.float32:
+            self.policy = self.policy.to(memory_format=torch.channels_last)
+
+    @torch.no_grad()
+    def __call__(self, x, priors_out, values_out):
+        if self.dtype != torch.float32:
+            with torch.autocast("cuda", dtype=self.dtype):
+                logits, value = self.policy(x)
+        else:
+            logits, value = self.policy(x)
+        torch.softmax(logits.float(), dim=-1, out=priors_out)
+        values_out.copy_(value.float().reshape(-1))
+
+
+class SelfPlayRunner:
+    """Batched replacement of ``Trainer.collect_self_play_games`` (train.py:199-225):
+    plays ``n_slots`` concurrent games with one network evaluation per simulation per game."""
+
+    def __init__(self, engine, evaluator=None, use_graph=True):
+        self.e = engine
+        self.evaluator = evaluator
+        self.external = engine.cfg.eval_kind == _lib.EVAL_EXTERNAL
+        assert not self.external or evaluator is not None
+        self.use_graph = use_graph
+        self.graph = None
+
+    def _iteration(self):
+        if self.external:
+            self.evaluator(self.e.nn_input, self.e.priors, self.e.values)
+        self.e.step()
+
+    def warm_start(self):
+        self.e.reset()
+        self.e.step()  # emits the root leaves
+
+    def run_iterations(self, n):
+        if self.use_graph and self.graph is None:
+            s = torch.cuda.Stream(device=self.e.device)
+            s.wait_stream(torch.cuda.current_stream(self.e.device))
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._iteration()
+            torch.cuda.current_stream(self.e.device).wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._iteration()
+            self.graph = g
+            n -= 3
+        for _ in range(max(n, 0)):
+            if self.graph is not None:
+                self.graph.replay()
+                self.e.launches += 1
+            else:
+                self._iteration()
+
+    def play(self, check_every=64, max_iterations=None):
+        """Run until every slot is DONE; returns the drained replay tuples."""
+        self.warm_start()
+        it = 0
+        while True:
+            self.run_iterations(check_every)
+            it += check_every
+            c = self.e.counters()
+            if c["errors"]:
+                self.e.raise_on_error()
+            if c["active"] == 0:
+                break
+            if max_iterations is not None and it >= max_iterations:
+                break
+        return self.e.drain()
+
+
+def split_games(out):
+    """Drained output -> the reference's per-game lists of (state int8[8,8], pi f32[65], value float)
+    (self_play_worker.py:31,85-86), ordered by game id."""
+    games = out["games"].numpy() if hasattr(out["games"], "numpy") else np.asarray(out["games"])
+    states = out["states"].numpy()
+    pis = out["pis"].numpy()
+    values = out["values"].numpy()
+    res = []
+    for gid, first, n, _w in sorted(map(tuple, games)):
+        res.append([(states[first + t].copy(), pis[first + t].copy(), float(values[first + t])) for t in range(n)])
+    return res

@@ -1,0 +1,272 @@
+/*
+ * othello_b200.h -- C ABI of libothello_b200.so, the B200 (sm_100a) self-play
+ * hot path behind the call surface of AfoninAndrei/alphaZero-Othello.
+ *
+ * The reference is pure Python and has no FFI; its boundary is duck typing on
+ * three surfaces (envs/game.py:5-57 as implemented by envs/othello.py:309-460,
+ * MCTS_model.py:172-274, self_play_worker.py:38-88).  Each entry point below
+ * names the reference code it replaces.  INTEGRATION.md shows the ctypes
+ * binding a maintainer adds.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; `stream` is a cudaStream_t passed as void*
+ *    (NULL = the legacy default stream);
+ *  - oth_* functions without "_host" take DEVICE pointers, never allocate and
+ *    never synchronise: the caller owns every buffer (oth_mcts_buffer_bytes
+ *    tells it how large each must be);
+ *  - oth_host_* functions take HOST pointers and do H2D copy, kernel, D2H copy
+ *    and a stream synchronise inside the call;
+ *  - return value 0 = OK, < 0 = an OTH_E_* code (oth_error_string decodes);
+ *  - bitboards: bit i = square index i = row*8+col = the Game API's action
+ *    index; `own` = discs of the side to move, `opp` = the other side.
+ */
+#ifndef OTHELLO_B200_H
+#define OTHELLO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OTH_ABI_VERSION 1
+#define OTH_NUM_ACTIONS 65 /* envs/othello.py:325 action_size: 64 squares + pass */
+#define OTH_PASS 64
+#define OTH_MAX_PLIES 128 /* trace / trajectory rows per game */
+#define OTH_MAX_CHILDREN 40 /* >= 33, the largest legal-move count on 8x8 */
+
+enum {
+    OTH_OK = 0,
+    OTH_E_CUDA = -1,     /* a CUDA runtime call failed (see oth_last_cuda_error) */
+    OTH_E_ARG = -2,      /* bad argument */
+    OTH_E_ILLEGAL = -3,  /* illegal move: the reference's ValueError, envs/othello.py:419-421 */
+    OTH_E_NO_DEVICE = -4 /* no CUDA device: there is no CPU fallback */
+};
+
+/* step flags (oth_step / oth_host_next_state out_flags) */
+#define OTH_F_ILLEGAL 1u  /* action not legal: outputs hold the unchanged position */
+#define OTH_F_TERMINAL 2u /* neither side can move after the action */
+#define OTH_F_WIN 4u      /* terminal and the mover has more discs */
+#define OTH_F_LOSS 8u     /* terminal and the mover has fewer discs */
+#define OTH_F_MUST_PASS 16u /* next side to move has no board move (and game not over) */
+
+int oth_abi_version(void);
+const char* oth_error_string(int code);
+const char* oth_last_cuda_error(void);
+int oth_device_count(void);
+
+/* ------------------------------------------------------------------ env -- */
+
+/* _BitBoard.valid_mask / _legal_moves, envs/othello.py:157-169, batched. */
+int oth_legal_moves(const uint64_t* own, const uint64_t* opp, uint64_t* out_moves, int64_t n, void* stream);
+
+/* _BitBoard.make_move (envs/othello.py:171-200) + the terminal test of
+ * get_value_and_terminated (:435-454), batched.  action 0..63 or 64 = pass.
+ * Outputs are from the NEXT mover's perspective (sides swapped), plus that
+ * mover's legal set and OTH_F_* flags (value is from the MOVER's side, as
+ * self_play_worker.py:78-82 reads it). */
+int oth_step(const uint64_t* own, const uint64_t* opp, const uint8_t* action, uint64_t* out_own, uint64_t* out_opp,
+             uint64_t* out_moves, uint8_t* out_flags, int64_t n, void* stream);
+
+/* Config C1: n_games uniform-random playouts from the start position, one
+ * thread per game, whole game in registers (the loop of
+ * envs/test_equivalence_game.py:158-190 / MCTS._rollout MCTS_model.py:276-303).
+ * Game g draws from Philox4x32-10 keyed (seed; game_id_base+g, ply).
+ * out_score[g]  = final disc difference for +1 (get_score(state, 1)),
+ * out_plies[g]  = plies played (passes count), out_final[2g..] = (+1 discs,
+ * -1 discs).  The first n_trace games also write their action per ply to
+ * trace_actions[g][OTH_MAX_PLIES] (0xFF padded) and the mover's legal set to
+ * trace_moves[g][OTH_MAX_PLIES].  counters[0] += total plies. Any output
+ * pointer may be NULL. */
+int oth_rollout(uint64_t seed, uint64_t game_id_base, int64_t n_games, int32_t* out_score, int32_t* out_plies,
+                uint64_t* out_final, int64_t n_trace, uint8_t* trace_actions, uint64_t* trace_moves,
+                unsigned long long* counters, void* stream);
+
+/* OthelloGameNew._np_to_bitboards / _bitboards_to_np, envs/othello.py:358-388:
+ * int8[n,64] boards (+ the player whose discs become `own`) <-> bitboards. */
+int oth_pack_states(const int8_t* states, const int8_t* players, uint64_t* own, uint64_t* opp, int64_t n, void* stream);
+int oth_unpack_states(const uint64_t* own, const uint64_t* opp, const int8_t* players, int8_t* states, int64_t n,
+                      void* stream);
+
+/* get_valid_moves on int8 boards, envs/othello.py:394-411: uint8[n,65]. */
+int oth_valid_moves_i8(const int8_t* states, const int8_t* players, uint8_t* out_masks, int64_t n, void* stream);
+
+/* get_random_symmetry (envs/othello.py:501-526) / get_symmetries (:286-298)
+ * for given per-sample k (quarter turns, np.rot90) and flip (np.fliplr):
+ * float32 boards [n,64] and policies [n,65]. */
+int oth_symmetry(const int8_t* states, const float* pis, const int32_t* ks, const uint8_t* flips, float* out_states,
+                 float* out_pis, int64_t n, void* stream);
+
+/* Host-buffer forms of the Game API (what envs.othello.OthelloGameNew calls). */
+int oth_host_valid_moves(const int8_t* states, const int8_t* players, uint8_t* out_masks, int64_t n);
+int oth_host_next_state(const int8_t* states, const int32_t* actions, const int8_t* players, int8_t* out_states,
+                        uint8_t* out_flags, int64_t n);
+int oth_host_value_terminated(const int8_t* states, const int8_t* players, int8_t* out_values, uint8_t* out_terms,
+                              int64_t n);
+int oth_host_symmetry(const int8_t* states, const float* pis, const int32_t* ks, const uint8_t* flips,
+                      float* out_states, float* out_pis, int64_t n);
+int oth_host_rollout(uint64_t seed, uint64_t game_id_base, int64_t n_games, int32_t* out_score, int32_t* out_plies,
+                     uint64_t* out_final, int64_t n_trace, uint8_t* trace_actions, uint64_t* trace_moves,
+                     unsigned long long* total_plies, float* kernel_ms);
+
+/* INT32-ALU roofline probe: dependent-free LOP3/IADD3/SHF mix; returns the
+ * measured thread-instructions per second in *out_ips. */
+int oth_host_int32_peak(double* out_ips, float* kernel_ms);
+
+/* ----------------------------------------------------------------- MCTS -- */
+
+/* evaluator kinds */
+#define OTH_EVAL_EXTERNAL 0 /* policy/value net outside the library (PyTorch) */
+#define OTH_EVAL_STUB_A 1   /* uniform priors, value 0 */
+#define OTH_EVAL_STUB_B 2   /* weighted-sum stub */
+#define OTH_EVAL_STUB_H 3   /* hash stub (oracle/othello_oracle.c orc_stub_h) */
+
+/* per-slot phases (oth_mcts_ctl.phase) */
+#define OTH_PH_RUN 0       /* searching, nothing pending */
+#define OTH_PH_WAIT_EVAL 1 /* a leaf sits in nn_input[slot]; needs priors/values[slot] */
+#define OTH_PH_IDLE 2      /* manual mode: num_simulations done, waiting for oth_mcts_advance */
+#define OTH_PH_DONE 3      /* self-play mode: this slot has played all its games */
+#define OTH_PH_ERROR 4     /* see ctl.error */
+
+/* ctl.error bits */
+#define OTH_ERR_NODE_OVERFLOW 1
+#define OTH_ERR_PATH_OVERFLOW 2
+#define OTH_ERR_OUT_OVERFLOW 4
+#define OTH_ERR_PLY_OVERFLOW 8
+#define OTH_ERR_BAD_ACTION 16 /* MCTS.make_move KeyError, MCTS_model.py:214 */
+
+typedef struct oth_mcts_config {
+    int32_t n_slots;          /* concurrent games on this GPU */
+    int32_t node_cap;         /* nodes per arena per slot (two arenas per slot) */
+    int32_t path_cap;         /* max search depth (<= 256) */
+    int32_t num_simulations;  /* args["num_simulations"], MCTS_model.py:237 */
+    int32_t num_exploratory_moves; /* self_play_worker.py:66-67 */
+    int32_t eval_kind;        /* OTH_EVAL_* */
+    int32_t self_play;        /* 1: moves are sampled and games restarted in-kernel (one_self_play);
+                                 0: manual -- the host calls oth_mcts_advance (MCTS.make_move) */
+    int32_t games_per_slot;   /* self-play: games each slot plays (<0 = endless) */
+    int32_t max_inline_sims;  /* simulations a slot may finish inside one launch without an
+                                 external evaluation (terminal hits; all of them with a stub) */
+    int32_t inject_random;    /* 1: read noise / u_move / u_tie from the buffers instead of Philox */
+    int32_t fused_softmax;    /* 1: `priors` holds logits; softmax is applied in-kernel */
+    int32_t lanes;            /* threads cooperating on one slot: 8, 16 or 32 */
+    int64_t out_pos_cap;      /* replay tuples the output ring can hold */
+    int64_t out_game_cap;     /* finished-game descriptors it can hold */
+    double c_puct;            /* args["c_puct"], MCTS_model.py:131,136 */
+    double dirichlet_alpha;   /* MCTS_model.py:341 */
+    double dirichlet_epsilon; /* MCTS_model.py:340-343 */
+    double temperature;       /* args["mcts_temperature"] */
+    double lambda;            /* args["lambda"], self_play_worker.py:8-35 */
+    uint64_t seed;            /* Philox key */
+    uint64_t game_id_base;    /* slot s plays games base + s + k*stride, k = 0.. */
+    uint64_t game_id_stride;
+    uint64_t stub_salt;       /* OTH_EVAL_STUB_H salt */
+} oth_mcts_config;
+
+/* 64-byte per-slot control block (device memory; readable by the host). */
+typedef struct oth_mcts_ctl {
+    int32_t phase;
+    int32_t root;      /* node index of the root in the current arena */
+    int32_t top;       /* bump pointer of the current arena */
+    int32_t arena;     /* 0/1 */
+    int32_t ply;
+    int32_t sims_done; /* simulations finished for the current move */
+    int32_t pending;   /* leaf awaiting evaluation */
+    int32_t path_len;
+    int32_t flags;     /* bit0 pending is a root initialisation (not a simulation); bit1 root priors are float64 */
+    int32_t player;    /* colour to move at the root: +1 / -1 */
+    int32_t games_left;
+    int32_t error;
+    int64_t game_id;
+    int64_t reserved;
+} oth_mcts_ctl;
+
+/* Device buffers the engine works on; sizes from oth_mcts_buffer_bytes(). */
+enum {
+    OTH_BUF_NODES = 0,   /* 32 B/node  [slot][2][node_cap] */
+    OTH_BUF_BOARDS,      /* 16 B/node  [slot][2][node_cap] */
+    OTH_BUF_CTL,         /* oth_mcts_ctl [slot] */
+    OTH_BUF_PATH,        /* int32 [slot][path_cap] */
+    OTH_BUF_ROOT_PRIOR64,/* double [slot][OTH_MAX_CHILDREN] */
+    OTH_BUF_NOISE,       /* double [slot][65]  Dirichlet draw used at ply 0 (recorded, or injected) */
+    OTH_BUF_U_MOVE,      /* double [slot][OTH_MAX_PLIES] np.random.choice(65,p) uniform per ply */
+    OTH_BUF_U_TIE,       /* double [slot][OTH_MAX_PLIES] temp~0 tie-pick uniform per ply */
+    OTH_BUF_TRAJ_BOARD,  /* 16 B [slot][OTH_MAX_PLIES] canonical position per ply */
+    OTH_BUF_TRAJ_PI,     /* float [slot][OTH_MAX_PLIES][65] */
+    OTH_BUF_TRAJ_ROOTV,  /* double [slot][OTH_MAX_PLIES] mcts.root.value after the search */
+    OTH_BUF_TRAJ_META,   /* int32 [slot][OTH_MAX_PLIES]: player (low byte, signed) | action << 8 */
+    OTH_BUF_OUT_BOARD,   /* 16 B [out_pos_cap] */
+    OTH_BUF_OUT_PI,      /* float [out_pos_cap][65] */
+    OTH_BUF_OUT_VALUE,   /* double [out_pos_cap]  value target G_t */
+    OTH_BUF_OUT_META,    /* int64 [out_pos_cap]: game_id << 16 | ply << 8 | (player & 0xff) */
+    OTH_BUF_OUT_GAMES,   /* int64 [out_game_cap][4]: game_id, first position, n positions, winner */
+    OTH_BUF_COUNTERS,    /* uint64 [16], see OTH_CNT_* */
+    OTH_BUF_COUNT
+};
+
+enum {
+    OTH_CNT_SIMS = 0,     /* simulations completed */
+    OTH_CNT_EVALS,        /* leaves evaluated (network slots used) */
+    OTH_CNT_TERMINAL,     /* simulations that ended on a terminal node */
+    OTH_CNT_GAMES,        /* games finished */
+    OTH_CNT_POSITIONS,    /* replay tuples emitted since the last drain */
+    OTH_CNT_OUT_GAMES,    /* finished-game descriptors since the last drain */
+    OTH_CNT_MOVES,        /* moves played */
+    OTH_CNT_ERRORS,       /* slots that entered OTH_PH_ERROR */
+    OTH_CNT_MAX_TOP,      /* largest arena fill seen */
+    OTH_CNT_MAX_DEPTH,    /* deepest path seen */
+    OTH_CNT_NODES,        /* nodes created */
+    OTH_CNT_COPIED,       /* nodes copied by re-rooting */
+    OTH_CNT_WAITING,      /* slots in OTH_PH_WAIT_EVAL after the last launch */
+    OTH_CNT_ACTIVE,       /* slots not DONE/IDLE/ERROR after the last launch */
+    OTH_CNT_LEVELS,       /* tree levels descended (select steps) */
+    OTH_CNT_CHILDREN      /* child records scanned by select */
+};
+
+typedef struct oth_mcts_buffers {
+    void* buf[OTH_BUF_COUNT];
+} oth_mcts_buffers;
+
+int oth_mcts_buffer_bytes(const oth_mcts_config* cfg, int64_t* out_bytes /* [OTH_BUF_COUNT] */);
+
+/* Start every slot on a fresh game from the initial position (one_self_play's
+ * setup, self_play_worker.py:60-62) and zero the counters.  The first
+ * oth_mcts_step after it consumes nothing and emits the root leaves. */
+int oth_mcts_reset(const oth_mcts_config* cfg, const oth_mcts_buffers* b, void* stream);
+
+/* Manual mode: give every slot a new tree rooted at (own, opp) with `player`
+ * to move (MCTS.policy_improve_step's root creation, MCTS_model.py:223-228). */
+int oth_mcts_set_roots(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const uint64_t* own, const uint64_t* opp,
+                       const int8_t* players, void* stream);
+
+/* Manual mode: begin a search of num_simulations on every idle slot
+ * (MCTS.policy_improve_step, MCTS_model.py:234-242). */
+int oth_mcts_begin_search(const oth_mcts_config* cfg, const oth_mcts_buffers* b, void* stream);
+
+/* THE hot kernel. For each slot: consume priors[slot][65] / values[slot] for
+ * its pending leaf (expand + backup: MCTS_model.py:325-360, 146-169), then run
+ * PUCT descents (:362-395, 129-139) until a leaf needs the network -- its
+ * canonical plane goes to nn_input[slot] -- or the move's simulations are done,
+ * in which case (self-play mode) the policy target is formed (:244-274), the
+ * move sampled (self_play_worker.py:64-88), the tree re-rooted (:200-215) and
+ * finished games are emitted with their lambda-returns (:8-35). */
+int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const float* priors, const float* values,
+                  float* nn_input, void* stream);
+
+/* Manual mode: MCTS.make_move (MCTS_model.py:200-215) on every slot;
+ * actions[slot] < 0 leaves that slot alone. */
+int oth_mcts_advance(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const int32_t* actions, void* stream);
+
+/* mcts.root.* as the reference exposes it: child visit counts / values /
+ * priors by action, root value and visit count, root position. NULL = skip. */
+int oth_mcts_root_stats(const oth_mcts_config* cfg, const oth_mcts_buffers* b, int32_t* counts, double* child_value,
+                        double* child_prior, double* root_value, int32_t* root_n, uint64_t* root_board, void* stream);
+
+/* Replay tuples -> the reference's array form: int8 [n,64] canonical states
+ * (state*player, self_play_worker.py:72) from packed boards. */
+int oth_unpack_canonical(const uint64_t* boards /* [n][2] own,opp */, int8_t* states, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTHELLO_B200_H */

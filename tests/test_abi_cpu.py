@@ -1,0 +1,70 @@
+"""CPU-side checks: the C-ABI library builds for sm_100a, loads, and exports every
+symbol include/othello_b200.h declares (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from alphazero_othello_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "othello_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(oth_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_loads():
+    path = build.build()
+    assert os.path.exists(path)
+    assert _lib.lib().oth_abi_version() == 1
+
+
+def test_every_header_symbol_is_exported_and_bound():
+    L = ctypes.CDLL(build.build())
+    names = _header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in othello_b200.h but not exported"
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS)
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.MctsCtl) == 64
+    assert ctypes.sizeof(_lib.MctsConfig) == 12 * 4 + 2 * 8 + 5 * 8 + 4 * 8
+    assert ctypes.sizeof(_lib.MctsBuffers) == 8 * _lib.BUF_COUNT
+
+
+def test_argument_validation_without_device():
+    L = _lib.lib()
+    assert L.oth_legal_moves(None, None, None, -1, None) == _lib.OTH_E_ARG
+    assert L.oth_legal_moves(None, None, None, 0, None) == _lib.OTH_OK
+    cfg = _lib.MctsConfig()
+    sizes = (ctypes.c_int64 * _lib.BUF_COUNT)()
+    assert L.oth_mcts_buffer_bytes(ctypes.byref(cfg), sizes) == _lib.OTH_E_ARG
+    cfg.n_slots, cfg.node_cap, cfg.path_cap, cfg.num_simulations, cfg.max_inline_sims, cfg.lanes = 4, 256, 64, 10, 4, 32
+    cfg.self_play, cfg.out_pos_cap, cfg.out_game_cap = 1, 1000, 10
+    assert L.oth_mcts_buffer_bytes(ctypes.byref(cfg), sizes) == 0
+    assert sizes[_lib.BUF_NODES] == 4 * 2 * 256 * 32 and sizes[_lib.BUF_BOARDS] == 4 * 2 * 256 * 16
+    assert L.oth_error_string(_lib.OTH_E_ILLEGAL).decode() == "Illegal move"
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from alphazero_othello_b200.envs.othello import OthelloGameNew
+    with pytest.raises(_lib.OthelloB200Error):
+        OthelloGameNew(8)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "alphazero_othello_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f

@@ -1,0 +1,236 @@
+"""GPU parity of the MCTS / self-play kernels through the C ABI: bit-exact visit counts,
+root values and value targets against results of the reference itself (tests/golden)
+and against the CPU oracle on the engine's own recorded randomness."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LANES = [32, 8]
+
+
+def _pack(state, player):
+    own = opp = 0
+    for i, v in enumerate((np.asarray(state).astype(np.int64) * int(player)).ravel()):
+        if v == 1:
+            own |= 1 << i
+        elif v == -1:
+            opp |= 1 << i
+    return own, opp
+
+
+def _i64(x):
+    return np.array([x], np.uint64).view(np.int64)
+
+
+def _manual_engine(cfg, lanes, n_slots=1, **kw):
+    from alphazero_othello_b200 import _lib
+    from alphazero_othello_b200.engine import MctsEngine
+    sid, sims, c, eps, alpha = int(cfg[0]), int(cfg[1]), cfg[2], cfg[3], cfg[4]
+    args = {"c_puct": c, "num_simulations": sims, "dirichlet_alpha": alpha, "dirichlet_epsilon": eps}
+    return MctsEngine(n_slots, args, self_play=False, eval_kind=[_lib.EVAL_STUB_A, _lib.EVAL_STUB_B, _lib.EVAL_STUB_H][sid],
+                      inject_random=True, lanes=lanes, stub_salt=int(cfg[6]), max_inline_sims=1000, **kw)
+
+
+def _search(e):
+    from alphazero_othello_b200 import _lib
+    e.begin_search()
+    for _ in range(64):
+        e.step()
+        if (e.ctl()["phase"] != _lib.PH_RUN).all():
+            break
+    e.raise_on_error()
+    assert (e.ctl()["phase"] == _lib.PH_IDLE).all()
+
+
+@pytest.mark.parametrize("lanes", LANES)
+@pytest.mark.parametrize("case", ["A", "B", "H_noise", "H_t0", "H_alpha", "B_long"])
+def test_visit_counts_match_reference(golden, case, lanes):
+    import torch
+    pre = f"mcts_{case}_"
+    cfg = golden[pre + "cfg"]
+    e = _manual_engine(cfg, lanes)
+    own, opp = _pack(golden[pre + "state"][0], golden[pre + "player"][0])
+    e.set_roots(torch.from_numpy(_i64(own)).cuda(), torch.from_numpy(_i64(opp)).cuda(),
+                torch.tensor([int(golden[pre + "player"][0])], dtype=torch.int8, device="cuda"))
+    n = len(golden[pre + "action"])
+    for t in range(n):
+        if golden[pre + "noise_used"][t]:
+            e.noise[0] = torch.from_numpy(golden[pre + "noise"][t]).cuda()
+        _search(e)
+        st = {k: v.cpu().numpy()[0] for k, v in e.root_stats().items()}
+        assert np.array_equal(st["counts"], golden[pre + "counts"][t]), (case, t)
+        assert st["root_n"] == golden[pre + "root_n"][t]
+        assert st["root_value"] == golden[pre + "root_value"][t]
+        assert np.array_equal(st["child_value"], golden[pre + "cval"][t])
+        assert np.array_equal(st["child_prior"], golden[pre + "cpri"][t])
+        assert tuple(st["root_board"].view(np.uint64)) == _pack(golden[pre + "state"][t], golden[pre + "player"][t])
+        e.advance(torch.tensor([int(golden[pre + "action"][t])], dtype=torch.int32, device="cuda"))
+        e.raise_on_error()
+
+
+def test_make_move_on_unexpanded_action_is_keyerror(golden):
+    import torch
+    e = _manual_engine(golden["mcts_A_cfg"], 32)
+    own, opp = _pack(golden["mcts_A_state"][0], 1)
+    e.set_roots(torch.from_numpy(_i64(own)).cuda(), torch.from_numpy(_i64(opp)).cuda(),
+                torch.tensor([1], dtype=torch.int8, device="cuda"))
+    _search(e)
+    e.advance(torch.tensor([0], dtype=torch.int32, device="cuda"))  # square 0 is not a legal first move
+    with pytest.raises(KeyError):
+        e.raise_on_error()
+
+
+def _selfplay_engine(args, lanes, n_slots, inject, salt, seed=0, games_per_slot=1, **kw):
+    from alphazero_othello_b200 import _lib
+    from alphazero_othello_b200.engine import MctsEngine
+    return MctsEngine(n_slots, args, self_play=True, eval_kind=_lib.EVAL_STUB_H, inject_random=inject, lanes=lanes,
+                      stub_salt=salt, seed=seed, games_per_slot=games_per_slot, **kw)
+
+
+def _run_to_done(e, max_launches=20000):
+    from alphazero_othello_b200 import _lib
+    e.reset()
+    for i in range(max_launches):
+        e.step()
+        if i % 16 == 15:
+            c = e.counters()
+            if c["errors"]:
+                e.raise_on_error()
+            if c["active"] == 0:
+                return
+    raise AssertionError("self-play did not finish")
+
+
+@pytest.mark.parametrize("lanes", LANES)
+@pytest.mark.parametrize("case", ["sp0", "sp1", "sp2", "sp3"])
+def test_self_play_matches_reference(golden, case, lanes):
+    import torch
+    from alphazero_othello_b200.engine import split_games
+    pre = f"sp_{case}_"
+    salt, sims, c, eps, alpha, temp, nexp, lam = golden[pre + "cfg"]
+    args = {"c_puct": c, "num_simulations": int(sims), "dirichlet_alpha": alpha, "dirichlet_epsilon": eps,
+            "mcts_temperature": temp, "num_exploratory_moves": int(nexp), "lambda": lam}
+    e = _selfplay_engine(args, lanes, 1, True, int(salt))
+    T = len(golden[pre + "values"])
+    e.noise[0] = torch.from_numpy(golden[pre + "noise"]).cuda()
+    e.u_move[0, :T] = torch.from_numpy(golden[pre + "u_move"]).cuda()
+    e.u_tie[0, :T] = torch.from_numpy(golden[pre + "u_tie"]).cuda()
+    _run_to_done(e)
+    (traj,) = split_games(e.drain())
+    assert len(traj) == T
+    assert np.array_equal(np.stack([t[0] for t in traj]), golden[pre + "states"])
+    pis = np.stack([t[1] for t in traj])
+    if temp == 1.0:
+        assert np.array_equal(pis, golden[pre + "pis"])
+    else:
+        assert np.abs(pis - golden[pre + "pis"]).max() <= 1e-6  # policy targets within 1e-6 (north_star)
+    assert np.array_equal(np.array([t[2] for t in traj]), golden[pre + "values"])
+
+
+@pytest.mark.parametrize("lanes", LANES)
+def test_self_play_vs_oracle_on_engine_randomness(lanes):
+    """Many concurrent games with the engine's own Philox noise / uniforms; the oracle replays
+    each game from the recorded draws and must reproduce every tuple bit for bit."""
+    import oracle as O
+    from alphazero_othello_b200.engine import split_games
+    args = {"c_puct": 2.0, "num_simulations": 48, "dirichlet_alpha": 1.0, "dirichlet_epsilon": 0.3,
+            "mcts_temperature": 1.0, "num_exploratory_moves": 20, "lambda": 0.98}
+    n = 96
+    e = _selfplay_engine(args, lanes, n, False, 99, seed=1234)
+    _run_to_done(e)
+    noise = e.noise.cpu().numpy(); um = e.u_move.cpu().numpy(); ut = e.u_tie.cpu().numpy()
+    out = e.drain()
+    games = split_games(out)
+    ids = sorted(int(g[0]) for g in out["games"].numpy())
+    assert ids == list(range(n)) and len(games) == n
+    c = e.counters()
+    assert c["games"] == n and c["errors"] == 0
+    tot_sims = 0
+    for g in range(n):
+        ref = O.self_play(args, O.Evaluator(stub=O.STUB_H, salt=99), noise[g], um[g], ut[g])
+        traj = games[g]
+        assert len(traj) == len(ref["values"]), g
+        assert np.array_equal(np.stack([t[0] for t in traj]), ref["states"]), g
+        assert np.array_equal(np.stack([t[1] for t in traj]), ref["pis"]), g
+        assert np.array_equal(np.array([t[2] for t in traj]), ref["values"]), g
+        tot_sims += ref["counters"]["sims"]
+    assert c["sims"] == tot_sims
+    assert not np.array_equal(noise[0], noise[1])
+
+
+def test_restart_and_game_ids_are_shard_independent():
+    """Slots restart with game_id += stride; a game's content depends only on its id, so two
+    'ranks' with half the slots each reproduce the single-engine run."""
+    from alphazero_othello_b200.engine import split_games
+    args = {"c_puct": 2.0, "num_simulations": 12, "dirichlet_alpha": 1.0, "dirichlet_epsilon": 0.3,
+            "mcts_temperature": 1.0, "num_exploratory_moves": 10, "lambda": 0.9}
+
+    def run(n_slots, base, stride, gps):
+        e = _selfplay_engine(args, 32, n_slots, False, 5, seed=77, games_per_slot=gps, game_id_base=base, game_id_stride=stride)
+        _run_to_done(e)
+        out = e.drain()
+        return {int(g[0]): t for g, t in zip(sorted(map(tuple, out["games"].numpy())), split_games(out))}
+
+    whole = run(8, 0, 8, 2)
+    assert sorted(whole) == list(range(16))
+    half0, half1 = run(4, 0, 8, 2), run(4, 4, 8, 2)
+    merged = {**half0, **half1}
+    assert sorted(merged) == sorted(whole)
+    for gid in whole:
+        a, b = whole[gid], merged[gid]
+        assert len(a) == len(b) and all(np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) and x[2] == y[2]
+                                        for x, y in zip(a, b))
+
+
+def test_external_evaluator_record_and_replay():
+    """The network path (WAIT_EVAL hand-off): a small torch module evaluates leaf batches; every
+    (position -> priors, value) it produced is recorded and served to the oracle."""
+    import torch
+    import oracle as O
+    from alphazero_othello_b200 import _lib
+    from alphazero_othello_b200.engine import MctsEngine, split_games
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(64, 96), torch.nn.Tanh(), torch.nn.Linear(96, 66)).cuda()
+    args = {"c_puct": 2.0, "num_simulations": 24, "dirichlet_alpha": 1.0, "dirichlet_epsilon": 0.3,
+            "mcts_temperature": 1.0, "num_exploratory_moves": 12, "lambda": 0.98}
+    n = 16
+    e = MctsEngine(n, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=1, seed=5)
+    table = O.EvalTable(1 << 18)
+    e.reset()
+    e.step()
+    w = (1 << (63 - np.arange(64, dtype=np.uint64)))  # the reference's bit numbering
+    for it in range(40000):
+        ph = e.ctl()["phase"]
+        if not ((ph == _lib.PH_RUN) | (ph == _lib.PH_WAIT_EVAL)).any():
+            break
+        with torch.no_grad():
+            y = net(e.nn_input.view(n, 64))
+            e.priors.copy_(torch.softmax(y[:, :65], -1))
+            e.values.copy_(torch.tanh(y[:, 65]))
+        x = e.nn_input.view(n, 64).cpu().numpy()
+        pr, va = e.priors.cpu().numpy(), e.values.cpu().numpy()
+        for s in np.nonzero(ph == _lib.PH_WAIT_EVAL)[0]:
+            own = int((w * (x[s] == 1)).sum()); opp = int((w * (x[s] == -1)).sum())
+            assert table.put(own, opp, pr[s], va[s]) in (0, 1)
+        e.step()
+    e.raise_on_error()
+    noise = e.noise.cpu().numpy(); um = e.u_move.cpu().numpy(); ut = e.u_tie.cpu().numpy()
+    games = split_games(e.drain())
+    assert len(games) == n
+    for g in range(n):
+        ref = O.self_play(args, O.Evaluator(table=table), noise[g], um[g], ut[g])
+        traj = games[g]
+        assert len(traj) == len(ref["values"])
+        assert np.array_equal(np.stack([t[0] for t in traj]), ref["states"])
+        assert np.array_equal(np.stack([t[1] for t in traj]), ref["pis"])
+        assert np.array_equal(np.array([t[2] for t in traj]), ref["values"])
+    assert table.misses == 0
+
+
+def test_node_overflow_fails_loudly():
+    from alphazero_othello_b200 import _lib
+    args = {"c_puct": 2.0, "num_simulations": 200, "dirichlet_epsilon": 0.0}
+    e = _selfplay_engine(args, 32, 2, False, 1, node_cap=64)
+    with pytest.raises(_lib.OthelloB200Error, match="overflow"):
+        _run_to_done(e, 400)
