@@ -32,6 +32,14 @@ __global__ void __launch_bounds__(256) k_legal_moves(const u64* __restrict__ own
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = legal_moves(own[n - 1], opp[n - 1]);
 }
 
+// scalar form for buffers that are not 16-byte aligned
+__global__ void __launch_bounds__(256) k_legal_moves_scalar(const u64* __restrict__ own, const u64* __restrict__ opp,
+                                                            u64* __restrict__ out, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = legal_moves(own[i], opp[i]);
+}
+
 __device__ __forceinline__ void step_one(u64 o, u64 p, int a, u64& no, u64& np, u64& nm, unsigned& fl)
 {
     fl = 0;
@@ -371,8 +379,10 @@ extern "C" int oth_legal_moves(const uint64_t* own, const uint64_t* opp, uint64_
 {
     if (n < 0 || (n > 0 && (!own || !opp || !out))) return OTH_E_ARG;
     if (n == 0) return OTH_OK;
-    if ((((uintptr_t)own | (uintptr_t)opp | (uintptr_t)out) & 15) != 0) return OTH_E_ARG;  // 128-bit access
-    k_legal_moves<<<grid_for((n + 1) / 2, 256), 256, 0, (cudaStream_t)stream>>>((const u64*)own, (const u64*)opp, (u64*)out, n);
+    if ((((uintptr_t)own | (uintptr_t)opp | (uintptr_t)out) & 15) != 0)  // no 128-bit access possible
+        k_legal_moves_scalar<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const u64*)own, (const u64*)opp, (u64*)out, n);
+    else
+        k_legal_moves<<<grid_for((n + 1) / 2, 256), 256, 0, (cudaStream_t)stream>>>((const u64*)own, (const u64*)opp, (u64*)out, n);
     return cuda_status(cudaGetLastError());
 }
 

@@ -168,6 +168,7 @@ class BatchedOthello:
         return own, opp
 
     def legal_moves(self, own, opp):
+        own, opp = own.contiguous(), opp.contiguous()
         out = self.torch.empty_like(own)
         with self.torch.cuda.device(self.device):
             _lib.check(_lib.lib().oth_legal_moves(own.data_ptr(), opp.data_ptr(), out.data_ptr(), own.numel(), self._stream()))
@@ -175,6 +176,7 @@ class BatchedOthello:
 
     def step(self, own, opp, action):
         t = self.torch
+        own, opp, action = own.contiguous(), opp.contiguous(), action.contiguous()
         n = own.numel()
         no, np_, nm = t.empty_like(own), t.empty_like(own), t.empty_like(own)
         fl = t.empty(n, dtype=t.uint8, device=self.device)
