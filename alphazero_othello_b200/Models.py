@@ -1,0 +1,196 @@
+"""Policy/value networks at the engine boundary -- these STAY PyTorch (north_star).
+
+Architectures and parameter names follow the reference's ``Models.py`` so its
+checkpoints / ``state_dict()``s load unchanged (``FastOthelloNet`` :93-161, the
+"small" net; ``AlphaZeroNet`` :164-221, the "big" net) and so
+``one_self_play``'s ``policy_class(**policy_config)`` reconstruction works.
+The engine only needs ``policy(x[B,1,8,8]) -> (logits[B,65], value[B,1])``.
+
+``fold_for_inference`` builds the fast eval-mode twin the batched engine runs:
+BatchNorm folded into the convolutions, channels_last bf16, cuDNN's fused
+conv+bias+ReLU / conv+add+ReLU epilogues.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class Inference:
+    """Single-position evaluation, the signature MCTS programs against (Models.py:11-31)."""
+
+    @torch.no_grad()
+    def inference(self, state, current_player):
+        x = torch.from_numpy((current_player * np.asarray(state)).astype(np.float32))[None]
+        x = x.to(next(self.parameters()).device)
+        self.eval()
+        logits, value = self(x)
+        return self.softmax(logits)[0].cpu().numpy(), value[0, 0].cpu().numpy().item()
+
+
+def _conv_bn_relu(cin, cout):
+    return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=3, padding=1), nn.BatchNorm2d(cout), nn.ReLU())
+
+
+class ResidualBlock(nn.Module):
+    def __init__(self, channels):
+        super().__init__()
+        self.conv1 = nn.Conv2d(channels, channels, kernel_size=3, padding=1)
+        self.bn1 = nn.BatchNorm2d(channels)
+        self.conv2 = nn.Conv2d(channels, channels, kernel_size=3, padding=1)
+        self.bn2 = nn.BatchNorm2d(channels)
+
+    def forward(self, x):
+        y = F.relu(self.bn1(self.conv1(x)))
+        y = self.bn2(self.conv2(y))
+        return F.relu(y + x)
+
+
+class FastOthelloNet(nn.Module, Inference):
+    """Small net: conv-bn-relu, one residual block, conv-bn-relu, linear heads (640 514 parameters)."""
+
+    def __init__(self, board_size, action_size):
+        super().__init__()
+        self.board_size, self.action_size = board_size, action_size
+        self.initial_conv = _conv_bn_relu(1, 64)
+        self.res_block = ResidualBlock(64)
+        self.conv_add = _conv_bn_relu(64, 64)
+        flat = 64 * board_size * board_size
+        self.fc_policy = nn.Linear(flat, action_size)
+        self.fc_value1 = nn.Linear(flat, 64)
+        self.fc_value2 = nn.Linear(64, 1)
+        self.softmax = nn.Softmax(dim=-1)
+
+    def get_config(self):
+        return {"board_size": self.board_size, "action_size": self.action_size}
+
+    def forward(self, x):
+        if x.dim() == 3:
+            x = x.unsqueeze(1)
+        h = self.conv_add(self.res_block(self.initial_conv(x)))
+        h = h.reshape(h.size(0), -1)
+        return self.fc_policy(h), torch.tanh(self.fc_value2(F.relu(self.fc_value1(h))))
+
+
+class AlphaZeroNet(nn.Module, Inference):
+    """Big net: 3x3 stem, n residual blocks, 1x1-conv policy and value heads (1 505 480 parameters at 5x128)."""
+
+    def __init__(self, board_size, action_size, n_res_blocks=5, channels=128):
+        super().__init__()
+        self.board_size, self.action_size = board_size, action_size
+        self.n_res_blocks, self.channels = n_res_blocks, channels
+        self.conv0 = nn.Conv2d(1, channels, 3, padding=1, bias=False)
+        self.bn0 = nn.BatchNorm2d(channels)
+        self.res = nn.Sequential(*[ResidualBlock(channels) for _ in range(n_res_blocks)])
+        self.pol_conv = nn.Conv2d(channels, 2, 1, bias=False)
+        self.pol_bn = nn.BatchNorm2d(2)
+        self.pol_fc = nn.Linear(2 * board_size * board_size, action_size)
+        self.val_conv = nn.Conv2d(channels, 1, 1, bias=False)
+        self.val_bn = nn.BatchNorm2d(1)
+        self.val_fc1 = nn.Linear(board_size * board_size, 256)
+        self.val_fc2 = nn.Linear(256, 1)
+        self.softmax = nn.Softmax(dim=-1)
+
+    def get_config(self):
+        return {"board_size": self.board_size, "action_size": self.action_size, "n_res_blocks": self.n_res_blocks,
+                "channels": self.channels}
+
+    def forward(self, x):
+        if x.dim() == 3:
+            x = x.unsqueeze(1)
+        h = self.res(F.relu(self.bn0(self.conv0(x))))
+        p = F.relu(self.pol_bn(self.pol_conv(h)))
+        v = F.relu(self.val_bn(self.val_conv(h)))
+        p = self.pol_fc(p.reshape(p.size(0), -1))
+        v = torch.tanh(self.val_fc2(F.relu(self.val_fc1(v.reshape(v.size(0), -1)))))
+        return p, v
+
+
+# ----------------------------------------------------------- fast eval twin --
+def _fold(conv, bn):
+    """Eval-mode BatchNorm folded into the preceding convolution: (weight, bias) float32."""
+    w = conv.weight.detach().float()
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.size(0), device=w.device)
+    s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    return w * s.view(-1, 1, 1, 1), (b - bn.running_mean.detach().float()) * s + bn.bias.detach().float()
+
+
+class _FusedConv(nn.Module):
+    """3x3 / 1x1 convolution + bias (+ residual) + ReLU in one cuDNN call."""
+
+    def __init__(self, w, b, dtype):
+        super().__init__()
+        self.pad = w.size(-1) // 2
+        self.register_buffer("w", w.to(dtype).contiguous(memory_format=torch.channels_last))
+        self.register_buffer("b", b.to(dtype))
+
+    def forward(self, x, residual=None):
+        p = (self.pad, self.pad)
+        if residual is None:
+            return torch.cudnn_convolution_relu(x, self.w, self.b, (1, 1), p, (1, 1), 1)
+        return torch.cudnn_convolution_add_relu(x, self.w, residual, 1.0, self.b, (1, 1), p, (1, 1), 1)
+
+
+class FoldedNet(nn.Module):
+    """Inference-only twin of FastOthelloNet / AlphaZeroNet (same function up to dtype rounding)."""
+
+    def __init__(self, net, dtype=torch.bfloat16):
+        super().__init__()
+        self.dtype = dtype
+        self.kind = "big" if isinstance(net, AlphaZeroNet) or hasattr(net, "pol_conv") else "small"
+        mk = lambda c, bn: _FusedConv(*_fold(c, bn), dtype)
+        if self.kind == "small":
+            self.stem = mk(net.initial_conv[0], net.initial_conv[1])
+            self.blocks = nn.ModuleList([nn.ModuleList([mk(net.res_block.conv1, net.res_block.bn1),
+                                                        mk(net.res_block.conv2, net.res_block.bn2)])])
+            self.tail = mk(net.conv_add[0], net.conv_add[1])
+            # one GEMM for both heads: [policy(65) | value hidden(64)] over the NHWC-flattened features
+            wp, wv = net.fc_policy.weight.detach().float(), net.fc_value1.weight.detach().float()
+            w = torch.cat([wp, wv], 0).view(-1, 64, 8, 8).permute(0, 2, 3, 1).reshape(wp.size(0) + wv.size(0), -1)
+            self.register_buffer("head_w", w.to(dtype).contiguous())
+            self.register_buffer("head_b", torch.cat([net.fc_policy.bias, net.fc_value1.bias]).detach().to(dtype))
+            self.register_buffer("v2_w", net.fc_value2.weight.detach().to(dtype))
+            self.register_buffer("v2_b", net.fc_value2.bias.detach().to(dtype))
+        else:
+            self.stem = mk(net.conv0, net.bn0)
+            self.blocks = nn.ModuleList([nn.ModuleList([mk(b.conv1, b.bn1), mk(b.conv2, b.bn2)]) for b in net.res])
+            # both 1x1 head convolutions as one 3-channel convolution
+            pw, pb = _fold(net.pol_conv, net.pol_bn)
+            vw, vb = _fold(net.val_conv, net.val_bn)
+            self.heads = _FusedConv(torch.cat([pw, vw], 0), torch.cat([pb, vb], 0), dtype)
+            self.pol_fc = net.pol_fc
+            self.val_fc1, self.val_fc2 = net.val_fc1, net.val_fc2
+        self.n_actions = net.action_size
+
+    @torch.no_grad()
+    def forward(self, x):
+        if x.dim() == 3:
+            x = x.unsqueeze(1)
+        h = x.to(self.dtype).contiguous(memory_format=torch.channels_last)
+        h = self.stem(h)
+        for c1, c2 in self.blocks:
+            h = c2(c1(h), residual=h)
+        if self.kind == "small":
+            h = self.tail(h)
+            y = F.linear(h.permute(0, 2, 3, 1).reshape(h.size(0), -1), self.head_w, self.head_b)
+            logits = y[:, :self.n_actions]
+            v = torch.tanh(F.linear(F.relu(y[:, self.n_actions:]), self.v2_w, self.v2_b))
+            return logits.float(), v.float()
+        y = self.heads(h).float()  # [B,3,8,8]: two policy planes, one value plane (ReLU applied)
+        p = self.pol_fc(y[:, :2].reshape(y.size(0), -1))
+        v = torch.tanh(self.val_fc2(F.relu(self.val_fc1(y[:, 2].reshape(y.size(0), -1)))))
+        return p, v
+
+
+@torch.no_grad()
+def refold_(folded, net):
+    """Refresh a FoldedNet in place from (updated) weights of ``net`` -- same buffers, so a
+    captured CUDA graph that runs ``folded`` stays valid."""
+    fresh = FoldedNet(net.eval(), folded.dtype).to(next(net.parameters()).device)
+    for old, new in zip(folded.buffers(), fresh.buffers()):
+        old.copy_(new)
+    return folded
+
+
+def fold_for_inference(net, dtype=torch.bfloat16):
+    return FoldedNet(net.eval(), dtype).to(next(net.parameters()).device).eval()

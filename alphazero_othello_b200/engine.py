@@ -234,20 +234,24 @@ class SelfPlayRunner:
         self.e.reset()
         self.e.step()  # emits the root leaves
 
-    def run_iterations(self, n):
-        if self.use_graph and self.graph is None:
-            s = torch.cuda.Stream(device=self.e.device)
-            s.wait_stream(torch.cuda.current_stream(self.e.device))
-            with torch.cuda.stream(s):
-                for _ in range(2):
-                    self._iteration()
-            torch.cuda.current_stream(self.e.device).wait_stream(s)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+    def _capture(self):
+        dev = self.e.device
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):  # executed (they are real iterations), so lazy initialisation is done before capture
                 self._iteration()
-            self.graph = g
-            n -= 3
-        for _ in range(max(n, 0)):
+        torch.cuda.current_stream(dev).wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._iteration()  # recorded, not executed
+        self.graph = g
+
+    def run_iterations(self, n):
+        """n x (network forward over the leaf batch + one fused MCTS kernel launch), as CUDA-graph replays."""
+        if self.use_graph and self.graph is None:
+            self._capture()
+        for _ in range(n):
             if self.graph is not None:
                 self.graph.replay()
                 self.e.launches += 1

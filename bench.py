@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- MCTS self-play throughput of the B200 engine (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2] [--impl reference]
+
+A "step" = `iters_per_step` (= num_simulations) engine iterations: one policy/value forward
+over the leaf batch of every concurrent game + one launch of the fused MCTS kernel, i.e.
+about one move of search for every game.  Games start from the initial position, play
+themselves (moves sampled in-kernel, trees re-rooted, finished games emitted and restarted).
+
+One JSON line (rank 0):
+  value    whole-job simulations/s, everything resident in HBM, CUDA-graph replay
+  e2e      same through the host-facing call: per step H2D of the network weights from pinned
+           memory, the iterations, D2H of the step's policy targets / root values and of every
+           finished game's replay tuples
+  roofline the MCTS kernel against HBM: algorithmic bytes per launch (from the engine's own
+           counters, formula in DESIGN.md) / CUDA-event launch duration
+  cpu_baseline  the oracle port (C tree/env + the same torch net at batch 1) on the host cores
+  aux      config C1: env steps/s of the random-rollout kernel and its INT32 roofline
+`--impl reference` times the CPU port alone on the same config (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (description, net, concurrent games per GPU, sims/move)
+    "c4": ("big-model batched self-play, 16384 concurrent games, 400 sims/move", "big", 16384, 400),
+    "c3": ("small-model batched self-play, 4096 concurrent games, 200 sims/move", "small", 4096, 200),
+    "c2": ("small-model MCTS self-play, 100 sims/move, 1 game", "small", 1, 100),
+}
+TRAIN_ARGS = {"c_puct": 2.0, "dirichlet_alpha": 1.0, "dirichlet_epsilon": 0.3, "mcts_temperature": 1.0,
+              "num_exploratory_moves": 35, "lambda": 0.98}  # train.py:399-423 values
+
+
+def make_net(kind):
+    import torch
+    from alphazero_othello_b200.Models import AlphaZeroNet, FastOthelloNet
+    torch.manual_seed(0)
+    return (AlphaZeroNet(8, 65, 5, 128) if kind == "big" else FastOthelloNet(8, 65)).eval()
+
+
+# ------------------------------------------------------------------ CPU arm --
+def _cpu_worker(job):
+    kind, sims, n_search, warm = job
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    import oracle as O
+    net = make_net(kind)
+    ev = O.Evaluator(fn=net.inference)
+    g = O.OracleGame()
+    noise = np.random.RandomState(os.getpid()).dirichlet([1.0] * 65)
+    times = []
+    for i in range(warm + n_search):
+        m = O.OracleMCTS(TRAIN_ARGS["c_puct"], sims, ev, dirichlet_epsilon=TRAIN_ARGS["dirichlet_epsilon"])
+        t0 = time.perf_counter()
+        m.search(g.get_initial_state(), 1, noise)
+        times.append(time.perf_counter() - t0)
+    return times[warm:]
+
+
+def cpu_port_rate(kind, sims, steps, warm, cores):
+    """Oracle port on all host cores: every core runs `steps` searches of `sims` simulations
+    (one policy_improve_step each, batch-1 torch CPU forward per simulation as the reference does)."""
+    import multiprocessing as mp
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    with mp.get_context("spawn").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(kind, sims, steps, warm)] * cores)
+        wall = time.perf_counter() - t0
+    per_step = [max(r[i] for r in res) for i in range(steps)]  # slowest core per step
+    total = sum(per_step)
+    return cores * sims * steps / total, 1e3 * total / steps, wall
+
+
+# ---------------------------------------------------------------- utilities --
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.p = index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j].startswith("Active") for r in self.rows)]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(d, n_slots, launches):
+    """HBM bytes the MCTS kernel must move for the work the counters record (DESIGN.md 'Kernel roofline')."""
+    depth_nodes = d["levels"] + d["sims"]            # path entries = levels descended + the root of every simulation
+    b = 0
+    b += 32 * d["children"]                          # select: child records scanned (2 x 128-bit per child)
+    b += 32 * d["sims"]                              # select: root record
+    b += (12 + 12) * depth_nodes                     # backup: N (4 B) + W (8 B) read and written per path node
+    b += (4 + 4) * depth_nodes                       # path spilled to HBM across the network call, read back
+    b += d["evals"] * (16 + 16 + 32 + 8)             # leaf board (select + expand), leaf record, first_child/meta update
+    b += d["evals"] * (256 + 260 + 4)                # network input plane written, priors + value read
+    b += 48 * d["nodes"]                             # expansion: child record + child board written
+    b += (48 + 48) * d["copied"]                     # re-root: kept subtree read and written
+    b += d["moves"] * (32 * 12 + 260 + 32 + 16)      # policy target: root children, trajectory row
+    b += 2 * 64 * n_slots * launches                 # per-slot control block read and written every launch
+    return b
+
+
+# -------------------------------------------------------------- B200 arm ----
+def run_b200(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from alphazero_othello_b200 import _lib
+    from alphazero_othello_b200.Models import fold_for_inference, refold_
+    from alphazero_othello_b200.engine import BatchedPolicy, MctsEngine, SelfPlayRunner
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    desc, kind, G, sims = WORKLOADS[a.workload]
+    if a.games:
+        G = a.games
+    iters = a.iters_per_step or sims
+    args = dict(TRAIN_ARGS, num_simulations=sims)
+
+    net = make_net(kind)
+    # host copy of the weights (pinned), as Trainer.collect_self_play_games ships them (train.py:207-217)
+    flat_host = torch.cat([p.detach().reshape(-1) for p in net.state_dict().values() if p.dtype.is_floating_point]).pin_memory()
+    net = net.to(dev)
+    flat_dev = torch.empty_like(flat_host, device=dev)
+
+    folded = None
+
+    def load_weights():  # H2D (+ NCCL broadcast from rank 0 when sharded) and re-fold in place
+        flat_dev.copy_(flat_host, non_blocking=True)
+        if world > 1:
+            dist.broadcast(flat_dev, 0)
+        off = 0
+        for p in net.state_dict().values():
+            if p.dtype.is_floating_point:
+                n = p.numel()
+                p.copy_(flat_dev[off:off + n].view_as(p))
+                off += n
+        return fold_for_inference(net, torch.bfloat16) if folded is None else refold_(folded, net)
+
+    folded = load_weights()
+    ev = BatchedPolicy(folded, dev, torch.float32)
+    eng = MctsEngine(G, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=-1, device=dev, seed=a.seed,
+                     game_id_base=rank * G, game_id_stride=G * world, lanes=a.lanes, max_inline_sims=a.max_inline,
+                     out_pos_cap=G * 80, out_game_cap=G + 64)
+    run = SelfPlayRunner(eng, ev, use_graph=not a.no_graph)
+    run.warm_start()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        c0 = eng.counters()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        c1 = eng.counters()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, {k: c1[k] - c0[k] for k in c1}
+
+    def total(x):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return float(t)
+
+    def plain_step():
+        run.run_iterations(iters)
+
+    for _ in range(a.warmup):
+        plain_step()
+    eng.drain(to_host=False)
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms, d = timed(plain_step, a.steps)
+    clk = clocks.stop()
+    eng.raise_on_error()
+    sims_total = total(d["sims"])
+    value = sims_total / (ms * 1e-3)
+    eng.drain(to_host=False)
+
+    # ---- e2e: weights H2D (+broadcast), iterations, D2H of targets and finished games (+gather)
+    pin_counts = torch.empty((G, 65), dtype=torch.int32).pin_memory()
+    pin_rootv = torch.empty((G,), dtype=torch.float64).pin_memory()
+    io = {"h2d": 0, "d2h": 0}
+
+    def e2e_step():
+        load_weights()
+        io["h2d"] += flat_host.numel() * 4
+        run.run_iterations(iters)
+        st = eng.root_stats()
+        pin_counts.copy_(st["counts"], non_blocking=True)
+        pin_rootv.copy_(st["root_value"], non_blocking=True)
+        out = eng.drain(to_host=True)
+        io["d2h"] += pin_counts.numel() * 4 + pin_rootv.numel() * 8 + sum(v.numel() * v.element_size() for v in out.values())
+        if world > 1:  # replay gather to rank 0 (sizes, then padded payload)
+            n = torch.tensor([out["values"].numel()], device=dev)
+            ns = [torch.zeros_like(n) for _ in range(world)]
+            dist.all_gather(ns, n)
+            mx = max(int(x) for x in ns)
+            if mx:
+                pay = torch.zeros((mx, 65 + 4), dtype=torch.float32, device=dev)
+                k = out["values"].numel()
+                if k:
+                    pay[:k, :65] = out["pis"].to(dev)
+                    pay[:k, 65] = out["values"].to(dev).float()
+                    pay[:k, 66:68] = out["boards"].to(dev).view(torch.float32).view(k, 4)[:, :2]
+                lst = [torch.zeros_like(pay) for _ in range(world)] if rank == 0 else None
+                dist.gather(pay, lst, 0)
+        torch.cuda.synchronize(dev)
+
+    e2e_step()  # warm
+    io["h2d"] = io["d2h"] = 0
+    ms2, d2 = timed(e2e_step, a.steps)
+    e2e_value = total(d2["sims"]) / (ms2 * 1e-3)
+
+    # ---- roofline of the MCTS kernel: CUDA events around every launch, no graph
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(iters)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(iters)]
+    torch.cuda.synchronize(dev)
+    c0 = eng.counters()
+    for i in range(iters):
+        ev(eng.nn_input, eng.priors, eng.values)
+        ev0[i].record()
+        eng.step()
+        ev1[i].record()
+    torch.cuda.synchronize(dev)
+    c1 = eng.counters()
+    dk = {k: c1[k] - c0[k] for k in c1}
+    kms = sorted(x.elapsed_time(y) for x, y in zip(ev0, ev1))
+    k_avg = sum(kms) / len(kms)
+    alg = algorithmic_bytes(dk, G, iters) / iters
+    peak, peak_src = measured_peaks()
+    achieved = alg / (k_avg * 1e-3) / 1e9
+    eng.drain(to_host=False)
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": "MCTS simulations/s (self-play, one network evaluation per simulation)", "value": value,
+            "unit": "sims/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 search (u64 boards), bf16 network",
+            "data": "synthetic: self-play from the initial position, random-init weights (torch.manual_seed(0))",
+            "config": {"workload": f"{a.workload}: {desc}", "net": kind, "games_per_gpu": G, "sims_per_move": sims,
+                       "iters_per_step": iters, "lanes": a.lanes, "cuda_graph": not a.no_graph,
+                       "l2": f"tree arenas {eng.buf_bytes[0] + eng.buf_bytes[1] >> 20} MiB per GPU >> 126 MB L2 (inputs larger than L2)",
+                       "sharding": "games by id, no collective on the search path"},
+            "positions_per_s": total(d["moves"]) / (ms * 1e-3),
+            "e2e": {"value": e2e_value, "unit": "sims/s", "h2d_bytes_per_step": io["h2d"] // a.steps,
+                    "d2h_bytes_per_step": io["d2h"] // a.steps, "ms_per_step": ms2 / a.steps,
+                    "includes": "weights H2D from pinned host (+NCCL broadcast if sharded), BN re-fold, "
+                                "D2H of policy targets/root values and finished games' replay tuples (+gather to rank 0)"},
+            "gpu_launches": a.steps * iters,
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": f"k_mcts_step<{a.lanes}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg, "launch_ms_avg": k_avg, "launch_ms_median": kms[len(kms) // 2],
+                         "bytes_per_sim": algorithmic_bytes(dk, G, iters) / max(dk["sims"], 1),
+                         "kernel_share_of_iteration": k_avg / (ms / a.steps / iters)},
+            "search_counters_per_step": {k: d[k] / a.steps for k in ("sims", "evals", "terminal_sims", "moves", "games", "nodes", "copied", "levels", "children")},
+        }
+    if world > 1:
+        dist.barrier()
+    return out, dev
+
+
+def aux_env(dev):
+    """Config C1: random-rollout env throughput + INT32 roofline (rank 0, N=1)."""
+    import ctypes as C
+    import torch
+    from alphazero_othello_b200 import _lib
+    from alphazero_othello_b200.envs.othello import BatchedOthello
+    env = BatchedOthello(dev)
+    n = 1 << 22
+    best = None
+    for rep in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        r = env.rollout(n, seed=rep)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if rep and (best is None or ms < best[0]):
+            best = (ms, int(r["counters"][0]))
+    ips, kms = C.c_double(0), C.c_float(0)
+    _lib.check(_lib.lib().oth_host_int32_peak(C.byref(ips), C.byref(kms)))
+    # e2e through the host-buffer C-ABI call (results copied back to host arrays)
+    import numpy as np
+    sc, pl = np.empty(n, np.int32), np.empty(n, np.int32)
+    tot, k2 = C.c_ulonglong(0), C.c_float(0)
+    t0 = time.perf_counter()
+    _lib.check(_lib.lib().oth_host_rollout(9, 0, n, sc.ctypes.data, pl.ctypes.data, None, 0, None, None, C.byref(tot), C.byref(k2)))
+    t1 = time.perf_counter()
+    steps_s = best[1] / (best[0] * 1e-3)
+    return {"workload": "c1: Othello 8x8 random-policy rollouts, 2^22 games", "env_steps_per_s": steps_s, "kernel_ms": best[0],
+            "plies": best[1], "e2e_env_steps_per_s": tot.value / (t1 - t0), "e2e_d2h_bytes": n * 8,
+            "int32_roofline": {"bound": "int32-alu", "instr_per_ply": 600, "achieved_ginstr_s": steps_s * 600 / 1e9,
+                               "peak_ginstr_s": ips.value / 1e9, "frac": steps_s * 600 / ips.value,
+                               "peak_source": "measured live: LOP3+IADD3 probe kernel (oth_host_int32_peak)"}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--games", type=int, default=0, help="override concurrent games per GPU")
+    ap.add_argument("--iters-per-step", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=32)
+    ap.add_argument("--max-inline", type=int, default=8)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    desc, kind, G, sims = WORKLOADS[a.workload]
+    cores = len(os.sched_getaffinity(0))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        import oracle
+        oracle.build()
+        rate, ms_step, wall = cpu_port_rate(kind, sims, a.steps, a.warmup, cores)
+        sample = f"per step every core runs one policy_improve_step of {sims} simulations from the initial position " \
+                 f"(batch-1 torch CPU forward per simulation), {cores} processes"
+        print(json.dumps({
+            "impl": "reference", "metric": "MCTS simulations/s (self-play, one network evaluation per simulation)",
+            "value": rate, "unit": "sims/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 search, f32 network (CPU)",
+            "data": "synthetic: random-init weights (torch.manual_seed(0))",
+            "config": {"workload": f"{a.workload}: {desc}", "net": kind, "sims_per_move": sims},
+            "cpu_baseline": {"value": rate, "unit": "sims/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}), flush=True)
+        return
+
+    out, dev = run_b200(a)
+    if rank == 0:
+        if world == 1 and not a.no_aux:
+            out["aux"] = aux_env(dev)
+        if world == 1 and not a.no_cpu_baseline:
+            import oracle
+            oracle.build()
+            rate, ms_step, wall = cpu_port_rate(kind, sims, 2, 1, cores)
+            out["cpu_baseline"] = {"value": rate, "unit": "sims/s", "cores": cores, "kind": "port",
+                                   "sample": f"{cores} processes x 2 searches of {sims} simulations from the initial position "
+                                             f"(oracle C tree/env + batch-1 torch CPU forward of the {kind} net), {wall:.1f} s wall"}
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,121 @@
+"""The reference-facing Python surfaces (MCTS class, one_self_play, collect_self_play_games,
+network twins) on the GPU, checked like the reference's own call sites use them."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+class _StubH:
+    """Python twin of the oracle's hash stub with the Models.Inference.inference signature."""
+
+    def __init__(self, salt=0):
+        self.salt = salt
+
+    def load_state_dict(self, sd):
+        pass
+
+    def eval(self):
+        pass
+
+    def inference(self, state, player):
+        import oracle as O
+        pri = np.zeros(65, np.float32)
+        val = np.zeros(1, np.float64)
+        import ctypes as C
+        salt = C.c_uint64(self.salt)
+        s = np.ascontiguousarray(state, dtype=np.int8)
+        fn = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)(O.lib().orc_get_stub(O.STUB_H))
+        fn(C.addressof(salt), s.ctypes.data, int(player), pri.ctypes.data, val.ctypes.data)
+        return pri, float(val[0])
+
+
+@pytest.mark.parametrize("case", ["H_noise", "H_t0", "H_alpha"])
+def test_mcts_class_matches_reference_including_rng_stream(golden, case):
+    """Same np.random seed as the reference run that made the fixture -> same Dirichlet draw and
+    tie picks, bit-identical visit counts / root values / policy targets (even for temp != 1)."""
+    from alphazero_othello_b200.MCTS_model import MCTS
+    from alphazero_othello_b200.envs.othello import OthelloGameNew
+    pre = f"mcts_{case}_"
+    sid, sims, c, eps, alpha, temp, salt = (float(x) for x in golden[pre + "cfg"])  # Python floats, as the reference's callers pass
+    seed = {"H_noise": 3, "H_t0": 4, "H_alpha": 5}[case]
+    env = OthelloGameNew(8)
+    np.random.seed(seed)
+    m = MCTS(env, {"c_puct": c, "num_simulations": int(sims), "num_threads": 1}, _StubH(int(salt)), dirichlet_alpha=alpha,
+             dirichlet_epsilon=eps)
+    m.make_move(3)  # before any search: silent no-op (MCTS_model.py:209-211)
+    n = min(len(golden[pre + "action"]), 12)
+    for t in range(n):
+        s, pl = golden[pre + "state"][t], int(golden[pre + "player"][t])
+        probs = m.policy_improve_step(s, pl, temp=temp)
+        assert probs.dtype == np.float32 and np.array_equal(probs, golden[pre + "probs"][t]), (case, t)
+        assert m.root.value == golden[pre + "root_value"][t] and m.root.visit_count == golden[pre + "root_n"][t]
+        for a, ch in m.root.children.items():
+            assert ch.visit_count == golden[pre + "counts"][t][a] and ch.value == golden[pre + "cval"][t][a]
+            assert float(ch.prior) == golden[pre + "cpri"][t][a]
+        assert sorted(m.root.children) == list(np.nonzero(env.get_valid_moves(s, pl))[0])
+        m.make_move(int(golden[pre + "action"][t]))
+    with pytest.raises(AssertionError):  # tree/game state mismatch (MCTS_model.py:231-232)
+        m.policy_improve_step(golden[pre + "state"][0], int(golden[pre + "player"][0]))
+    with pytest.raises(KeyError):
+        bad = next(a for a in range(64) if a not in m.root.children)
+        m.make_move(bad)
+
+
+def test_one_self_play_matches_reference(golden):
+    from alphazero_othello_b200.self_play_worker import one_self_play
+    pre = "sp_sp0_"
+    salt, sims, c, eps, alpha, temp, nexp, lam = (float(x) for x in golden[pre + "cfg"])
+    args = {"c_puct": c, "num_simulations": int(sims), "num_threads": 1, "dirichlet_alpha": alpha, "dirichlet_epsilon": eps,
+            "mcts_temperature": temp, "num_exploratory_moves": int(nexp), "lambda": lam}
+    np.random.seed(10)  # the seed of the reference run (tests/golden/make_golden.py)
+    traj = one_self_play((8, args, (_StubH, {"salt": int(salt)}, {}), None))
+    assert len(traj) == len(golden[pre + "values"])
+    for t, (s, pi, v) in enumerate(traj):
+        assert s.dtype == np.int8 and np.array_equal(s, golden[pre + "states"][t])
+        assert pi.dtype == np.float32 and np.array_equal(pi, golden[pre + "pis"][t])
+        assert v == golden[pre + "values"][t]
+
+
+@pytest.mark.parametrize("kind", ["small", "big"])
+def test_folded_network_twin(kind):
+    import torch
+    from alphazero_othello_b200.Models import AlphaZeroNet, FastOthelloNet, fold_for_inference, refold_
+    torch.manual_seed(1)
+    net = (AlphaZeroNet(8, 65) if kind == "big" else FastOthelloNet(8, 65)).cuda().eval()
+    for m in net.modules():  # non-trivial BN statistics
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5); m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
+    x = torch.randint(-1, 2, (257, 1, 8, 8), device="cuda").float()
+    with torch.no_grad():
+        lr, vr = net(x)
+        l32, v32 = fold_for_inference(net, torch.float32)(x)
+        f16 = fold_for_inference(net, torch.bfloat16)
+        l16, v16 = f16(x)
+    assert (l32 - lr).abs().max() < 2e-3 and (v32 - vr).abs().max() < 2e-3
+    pr, p16 = torch.softmax(lr, -1), torch.softmax(l16, -1)
+    assert (p16 - pr).abs().max() < 0.05 and (v16 - vr).abs().max() < 0.08
+    with torch.no_grad():
+        net.val_fc2.bias.add_(0.5) if kind == "big" else net.fc_value2.bias.add_(0.5)
+        v_new = refold_(f16, net)(x)[1]
+    assert (v_new - v16).abs().max() > 1e-3
+
+
+def test_collect_self_play_games_small_net():
+    import torch
+    from alphazero_othello_b200.Models import FastOthelloNet
+    from alphazero_othello_b200.self_play_worker import collect_self_play_games
+    torch.manual_seed(0)
+    args = {"c_puct": 2.0, "num_simulations": 8, "dirichlet_alpha": 1.0, "dirichlet_epsilon": 0.3, "mcts_temperature": 1.0,
+            "num_exploratory_moves": 35, "lambda": 0.98}
+    games = collect_self_play_games(FastOthelloNet(8, 65), args, 48, n_slots=32)
+    assert len(games) == 48
+    for g in games:
+        assert 9 <= len(g) <= 128
+        s0, pi0, v0 = g[0]
+        assert s0.dtype == np.int8 and s0.shape == (8, 8) and np.abs(s0).sum() == 4
+        assert pi0.dtype == np.float32 and abs(pi0.sum() - 1) < 1e-5 and isinstance(v0, float)
+        assert set(np.nonzero(pi0)[0]) <= {19, 26, 37, 44}
+        assert g[-1][2] in (-1.0, 0.0, 1.0)
+        for (s, pi, v) in g:
+            assert abs(pi.sum() - 1) < 1e-5 and -1.0 <= v <= 1.0
