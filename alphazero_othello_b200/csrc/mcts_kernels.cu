@@ -113,13 +113,16 @@ struct Params {
 };
 
 // per-group scratch in shared memory
+enum { CNT_LOCAL = 16 };
+
 struct __align__(16) Scratch {
     double pri64[OTH_NUM_ACTIONS + 1];
     float pri[OTH_NUM_ACTIONS + 3];
     int path[256];
+    unsigned cnt[CNT_LOCAL];  // per-group event counters (lane 0 only), flushed once per launch
 };
 
-enum { CNT_LOCAL = 16 };
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int LANES>
 struct Ctx {
@@ -131,12 +134,20 @@ struct Ctx {
     Node* N;        // current arena
     ulonglong2* B;
     oth_mcts_ctl c;
-    unsigned long long cnt[CNT_LOCAL];
 
     __device__ Ctx(cg::thread_block_tile<LANES> t, const Params& p, Scratch& s) : tile(t), P(p), S(s), lane(t.thread_rank()), slot(0)
     {
-#pragma unroll
-        for (int i = 0; i < CNT_LOCAL; i++) cnt[i] = 0;
+        for (int i = lane; i < CNT_LOCAL; i += LANES) S.cnt[i] = 0;
+        tile.sync();
+    }
+
+    __device__ __forceinline__ void count(int which, unsigned n = 1)
+    {
+        if (lane == 0) S.cnt[which] += n;
+    }
+    __device__ __forceinline__ void count_max(int which, unsigned v)
+    {
+        if (lane == 0 && v > S.cnt[which]) S.cnt[which] = v;
     }
 
     __device__ __forceinline__ void bind_arena()
@@ -287,10 +298,8 @@ struct Ctx {
     // create every child in ascending action order (Node.expand :146-158,
     // Node.__init__ :68-108 -- child boards, legal sets and terminal values
     // are computed here, one child per lane).
-    __device__ bool expand(int leaf, bool root_init)
+    __device__ bool expand(int leaf, bool root_init, const Node& lf, const ulonglong2 lb)
     {
-        const Node lf = load_node(N + leaf);
-        const ulonglong2 lb = B[leaf];
         const u64 own = lb.x, opp = lb.y;
         const u64 M = lf.moves;
         const bool is_pass = (M == 0);
@@ -357,7 +366,10 @@ struct Ctx {
         }
         c.top = fc + nchild;
         if (f64) c.flags |= 2;
-        cnt[OTH_CNT_NODES] += (lane == 0) ? nchild : 0;
+        if (root_init) {  // prefetch hints for the next launches (never read for semantics)
+            c.reserved = (long long)(unsigned)fc | ((long long)nchild << 32);
+        }
+        count(OTH_CNT_NODES, nchild);
         tile.sync();
         return true;
     }
@@ -438,16 +450,16 @@ struct Ctx {
                     bi = oi;
                 }
             }
-            const int src = bi % LANES;
+            const int src = bi & (LANES - 1);
             nd.N = tile.shfl(k_N, src);
             nd.first_child = tile.shfl(k_fc, src);
             nd.meta = tile.shfl(k_meta, src);
             nd.moves = tile.shfl(k_moves, src);
             cur = fc + bi;
-            if (lane == 0) {
-                cnt[OTH_CNT_LEVELS] += 1;
-                cnt[OTH_CNT_CHILDREN] += nchild;
-            }
+            // the chosen child's board is needed only if it turns out to be the leaf: start fetching it now
+            prefetch_l2(B + cur);
+            count(OTH_CNT_LEVELS);
+            count(OTH_CNT_CHILDREN, nchild);
         }
     }
 
@@ -475,6 +487,7 @@ struct Ctx {
         c.pending = -1;
         c.path_len = 0;
         c.flags = 0;
+        c.reserved = -1;
         c.phase = OTH_PH_RUN;
         tile.sync();
     }
@@ -534,10 +547,14 @@ struct Ctx {
             i += chunk;
             tile.sync();
         }
-        if (lane == 0) cnt[OTH_CNT_COPIED] += top;
+        count(OTH_CNT_COPIED, top);
         c.root = 0;
         c.top = top;
         c.flags &= ~2;
+        {  // prefetch hint: where the new root's children now live
+            const uint4 b = *(reinterpret_cast<const uint4*>(Nd) + 1);
+            c.reserved = (int)b.x >= 0 ? ((long long)b.x | ((long long)(b.y & 0xffu) << 32)) : -1;
+        }
     }
 
     // ------------------------------------------------ policy target etc --
@@ -663,7 +680,7 @@ struct Ctx {
         const float* sp = P.traj_pi + tb * OTH_NUM_ACTIONS;
         float* dp = P.out_pi + (size_t)base * OTH_NUM_ACTIONS;
         for (int e = lane; e < nply * OTH_NUM_ACTIONS; e += LANES) dp[e] = sp[e];
-        if (lane == 0) cnt[OTH_CNT_GAMES] += 1;
+        count(OTH_CNT_GAMES);
     }
 
     // One self-play ply after its search (self_play_worker.py:64-88).
@@ -696,8 +713,8 @@ struct Ctx {
             P.traj_board[tb + T] = B[c.root];
             P.traj_rootv[tb + T] = root.N ? __ddiv_rn(root.W, (double)root.N) : 0.0;  // mcts.root.value, :72-73
             P.traj_meta[tb + T] = (c.player & 0xff) | (action << 8);
-            cnt[OTH_CNT_MOVES] += 1;
         }
+        count(OTH_CNT_MOVES);
         // mcts.make_move(action): locate the child (KeyError if absent)
         const int fc = root.first_child, nchild = meta_nchild(root.meta);
         int ci = -1;
@@ -742,28 +759,53 @@ struct Ctx {
     // ------------------------------------------------------ slot driver --
     __device__ void run_slot()
     {
+        // (1) everything that depends only on the slot index is requested at once:
+        //     control block, network outputs for the pending leaf
+        constexpr int NPL = (OTH_NUM_ACTIONS + LANES - 1) / LANES;
+        const bool stub = P.cfg.eval_kind != OTH_EVAL_EXTERNAL;
+        float pv[NPL];
+        float nn_value = 0.0f;
+        if (!stub) {
+            const float* pr = P.priors + (size_t)slot * OTH_NUM_ACTIONS;
+#pragma unroll
+            for (int k = 0; k < NPL; k++) {
+                const int a = lane + k * LANES;
+                pv[k] = a < OTH_NUM_ACTIONS ? pr[a] : 0.0f;
+            }
+            nn_value = P.values[slot];
+        }
         c = P.ctl[slot];
         bind_arena();
-        const bool stub = P.cfg.eval_kind != OTH_EVAL_EXTERNAL;
         if (c.phase == OTH_PH_WAIT_EVAL) {
-            // network outputs for the pending leaf are in priors/values[slot]
-            const float* pr = P.priors + (size_t)slot * OTH_NUM_ACTIONS;
-            for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri[a] = pr[a];
+            // (2) second round trip: leaf record + board, the path, and L2 prefetches of what
+            //     backup and the next descent will touch (path nodes, root, root's children)
+            const Node lf = load_node(N + c.pending);
+            const ulonglong2 lb = B[c.pending];
             const int* gp = P.path + (size_t)slot * P.cfg.path_cap;
-            for (int d = lane; d < c.path_len; d += LANES) S.path[d] = gp[d];
-            const double value = (double)P.values[slot];
+            for (int d = lane; d < c.path_len; d += LANES) {
+                const int idx = gp[d];
+                S.path[d] = idx;
+                prefetch_l2(N + idx);
+            }
+            if (c.reserved >= 0) {
+                const int rfc = (int)(c.reserved & 0xffffffffLL), rn = (int)(c.reserved >> 32);
+                for (int i = lane; i < rn; i += LANES) prefetch_l2(N + rfc + i);
+            }
+#pragma unroll
+            for (int k = 0; k < NPL; k++) {
+                const int a = lane + k * LANES;
+                if (a < OTH_NUM_ACTIONS) S.pri[a] = pv[k];
+            }
             tile.sync();
             const bool root_init = c.flags & 1;
-            if (expand(c.pending, root_init)) {
-                backup(c.path_len, value);
+            if (expand(c.pending, root_init, lf, lb)) {
+                backup(c.path_len, (double)nn_value);
                 if (!root_init) {
                     c.sims_done++;
-                    if (lane == 0) cnt[OTH_CNT_SIMS] += 1;
+                    count(OTH_CNT_SIMS);
                 }
-                if (lane == 0) {
-                    cnt[OTH_CNT_EVALS] += 1;
-                    if ((unsigned long long)c.path_len > cnt[OTH_CNT_MAX_DEPTH]) cnt[OTH_CNT_MAX_DEPTH] = c.path_len;
-                }
+                count(OTH_CNT_EVALS);
+                count_max(OTH_CNT_MAX_DEPTH, (unsigned)c.path_len);
                 c.flags &= ~1;
                 c.pending = -1;
                 c.phase = OTH_PH_RUN;
@@ -788,26 +830,23 @@ struct Ctx {
                 backup(depth, (double)meta_tvalue(nd.meta));
                 c.sims_done++;
                 budget--;
-                if (lane == 0) {
-                    cnt[OTH_CNT_SIMS] += 1;
-                    cnt[OTH_CNT_TERMINAL] += 1;
-                }
+                count(OTH_CNT_SIMS);
+                count(OTH_CNT_TERMINAL);
                 continue;
             }
             const bool root_init = (depth == 1);  // the leaf is the root: policy_improve_step :234-235
             const ulonglong2 lb = B[leaf];
             if (stub) {
                 const double value = eval_stub(lb.x, lb.y);
-                if (!expand(leaf, root_init)) break;
+                nd.first_child = -1;
+                if (!expand(leaf, root_init, nd, lb)) break;
                 backup(depth, value);
                 if (!root_init) {
                     c.sims_done++;
-                    if (lane == 0) cnt[OTH_CNT_SIMS] += 1;
+                    count(OTH_CNT_SIMS);
                 }
-                if (lane == 0) {
-                    cnt[OTH_CNT_EVALS] += 1;
-                    if ((unsigned long long)depth > cnt[OTH_CNT_MAX_DEPTH]) cnt[OTH_CNT_MAX_DEPTH] = depth;
-                }
+                count(OTH_CNT_EVALS);
+                count_max(OTH_CNT_MAX_DEPTH, (unsigned)depth);
                 budget--;
                 continue;
             }
@@ -820,27 +859,26 @@ struct Ctx {
             int* gp = P.path + (size_t)slot * P.cfg.path_cap;
             for (int d = lane; d < depth; d += LANES) gp[d] = S.path[d];
         }
-        if (lane == 0) {
-            if (c.phase == OTH_PH_ERROR) cnt[OTH_CNT_ERRORS] += 1;
-            if (c.phase == OTH_PH_WAIT_EVAL) cnt[OTH_CNT_WAITING] += 1;
-            if (c.phase == OTH_PH_WAIT_EVAL || c.phase == OTH_PH_RUN) cnt[OTH_CNT_ACTIVE] += 1;
-            if ((unsigned long long)c.top > cnt[OTH_CNT_MAX_TOP]) cnt[OTH_CNT_MAX_TOP] = c.top;
-            P.ctl[slot] = c;
-        }
+        if (c.phase == OTH_PH_ERROR) count(OTH_CNT_ERRORS);
+        if (c.phase == OTH_PH_WAIT_EVAL) count(OTH_CNT_WAITING);
+        if (c.phase == OTH_PH_WAIT_EVAL || c.phase == OTH_PH_RUN) count(OTH_CNT_ACTIVE);
+        count_max(OTH_CNT_MAX_TOP, (unsigned)c.top);
+        if (lane == 0) P.ctl[slot] = c;
         tile.sync();
     }
 };
 
-__device__ __forceinline__ void flush_counters(unsigned long long* blk, const unsigned long long* cnt, unsigned long long* global,
-                                               bool leader)
+// Per-group counters -> one shared-memory reduction per block -> one global atomic per
+// counter per block.
+__device__ __forceinline__ void flush_counters(unsigned long long* blk, const unsigned* cnt, unsigned long long* global, bool leader)
 {
-    // block-level reduction in shared memory, then one global atomic per counter per block
     if (leader) {
 #pragma unroll
         for (int i = 0; i < CNT_LOCAL; i++) {
-            if (cnt[i] == 0) continue;
-            if (i == OTH_CNT_MAX_TOP || i == OTH_CNT_MAX_DEPTH) atomicMax(blk + i, cnt[i]);
-            else atomicAdd(blk + i, cnt[i]);
+            const unsigned v = cnt[i];
+            if (v == 0) continue;
+            if (i == OTH_CNT_MAX_TOP || i == OTH_CNT_MAX_DEPTH) atomicMax(blk + i, (unsigned long long)v);
+            else atomicAdd(blk + i, (unsigned long long)v);
         }
     }
     __syncthreads();
@@ -853,7 +891,7 @@ __device__ __forceinline__ void flush_counters(unsigned long long* blk, const un
 }
 
 template <int LANES>
-__global__ void __launch_bounds__(kBlock) k_mcts_step(const Params P)
+__global__ void __launch_bounds__(kBlock, 7) k_mcts_step(const Params P)
 {
     __shared__ Scratch scratch[kBlock / LANES];
     __shared__ unsigned long long blk_cnt[CNT_LOCAL];
@@ -866,7 +904,7 @@ __global__ void __launch_bounds__(kBlock) k_mcts_step(const Params P)
         ctx.slot = s;
         ctx.run_slot();
     }
-    flush_counters(blk_cnt, ctx.cnt, P.counters, ctx.lane == 0);
+    flush_counters(blk_cnt, ctx.S.cnt, P.counters, ctx.lane == 0);
 }
 
 // Start fresh games (self-play) on every slot.
@@ -957,7 +995,7 @@ __global__ void __launch_bounds__(kBlock) k_mcts_advance(const Params P, const i
         if (ctx.lane == 0) P.ctl[s] = ctx.c;
         tile.sync();
     }
-    flush_counters(blk_cnt, ctx.cnt, P.counters, ctx.lane == 0);
+    flush_counters(blk_cnt, ctx.S.cnt, P.counters, ctx.lane == 0);
 }
 
 template <int LANES>
