@@ -116,7 +116,9 @@ def _fold(conv, bn):
 
 
 class _FusedConv(nn.Module):
-    """3x3 / 1x1 convolution + bias (+ residual) + ReLU in one cuDNN call."""
+    """3x3 / 1x1 convolution + bias + ReLU in one cuDNN call; with a residual, cuDNN's plain
+    convolution followed by one in-place ``relu(x + bias + residual)`` pass
+    (``oth_nn_bias_add_relu_bf16``), which is faster than cuDNN's fused add-ReLU engine here."""
 
     def __init__(self, w, b, dtype):
         super().__init__()
@@ -128,7 +130,39 @@ class _FusedConv(nn.Module):
         p = (self.pad, self.pad)
         if residual is None:
             return torch.cudnn_convolution_relu(x, self.w, self.b, (1, 1), p, (1, 1), 1)
-        return torch.cudnn_convolution_add_relu(x, self.w, residual, 1.0, self.b, (1, 1), p, (1, 1), 1)
+        if x.dtype != torch.bfloat16:
+            return torch.cudnn_convolution_add_relu(x, self.w, residual, 1.0, self.b, (1, 1), p, (1, 1), 1)
+        y = F.conv2d(x, self.w, None, 1, self.pad)
+        assert y.is_contiguous(memory_format=torch.channels_last) and residual.is_contiguous(memory_format=torch.channels_last)
+        import ctypes as C
+        from . import _lib
+        _lib.check(_lib.lib().oth_nn_bias_add_relu_bf16(y.data_ptr(), residual.data_ptr(), self.b.data_ptr(), y.numel(),
+                                                        y.size(1), C.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)))
+        return y
+
+
+class _StemGemm(nn.Module):
+    """The 1-channel 3x3 stem as im2col + GEMM with a fused bias+ReLU epilogue: the output is
+    written straight in channels-last layout (cuDNN's 1-input-channel path is slow and NCHW)."""
+
+    def __init__(self, w, b, dtype):
+        super().__init__()
+        cout = w.size(0)
+        wt = torch.zeros(16, cout, dtype=torch.float32, device=w.device)  # K padded 9 -> 16 for alignment
+        wt[:9] = w.reshape(cout, 9).t()
+        self.register_buffer("wt", wt.to(dtype).contiguous())
+        self.register_buffer("b", b.to(dtype))
+        self.cout = cout
+
+    def forward(self, x):  # x [B,1,8,8] in self.wt.dtype
+        B = x.size(0)
+        cols = getattr(self, "_cols", None)
+        if cols is None or cols.size(0) != B or cols.dtype != x.dtype or cols.device != x.device:
+            cols = self._cols = torch.zeros(B, 8, 8, 16, dtype=x.dtype, device=x.device)  # K columns 9..15 stay zero
+        taps = F.pad(x[:, 0], (1, 1, 1, 1)).unfold(1, 3, 1).unfold(2, 3, 1)  # [B,8,8,3,3] view, no copy
+        cols[..., :9].unflatten(-1, (3, 3)).copy_(taps)  # one strided copy = im2col
+        y = torch._addmm_activation(self.b, cols.view(B * 64, 16), self.wt, use_gelu=False)  # relu epilogue
+        return y.view(B, 8, 8, self.cout).permute(0, 3, 1, 2)  # NHWC memory == channels_last [B,C,8,8]
 
 
 class FoldedNet(nn.Module):
@@ -139,8 +173,9 @@ class FoldedNet(nn.Module):
         self.dtype = dtype
         self.kind = "big" if isinstance(net, AlphaZeroNet) or hasattr(net, "pol_conv") else "small"
         mk = lambda c, bn: _FusedConv(*_fold(c, bn), dtype)
+        stem = (lambda c, bn: _StemGemm(*_fold(c, bn), dtype)) if dtype != torch.float32 else mk
         if self.kind == "small":
-            self.stem = mk(net.initial_conv[0], net.initial_conv[1])
+            self.stem = stem(net.initial_conv[0], net.initial_conv[1])
             self.blocks = nn.ModuleList([nn.ModuleList([mk(net.res_block.conv1, net.res_block.bn1),
                                                         mk(net.res_block.conv2, net.res_block.bn2)])])
             self.tail = mk(net.conv_add[0], net.conv_add[1])
@@ -152,7 +187,7 @@ class FoldedNet(nn.Module):
             self.register_buffer("v2_w", net.fc_value2.weight.detach().to(dtype))
             self.register_buffer("v2_b", net.fc_value2.bias.detach().to(dtype))
         else:
-            self.stem = mk(net.conv0, net.bn0)
+            self.stem = stem(net.conv0, net.bn0)
             self.blocks = nn.ModuleList([nn.ModuleList([mk(b.conv1, b.bn1), mk(b.conv2, b.bn2)]) for b in net.res])
             # both 1x1 head convolutions as one 3-channel convolution
             pw, pb = _fold(net.pol_conv, net.pol_bn)
@@ -166,8 +201,9 @@ class FoldedNet(nn.Module):
     def forward(self, x):
         if x.dim() == 3:
             x = x.unsqueeze(1)
-        h = x.to(self.dtype).contiguous(memory_format=torch.channels_last)
-        h = self.stem(h)
+        h = self.stem(x.to(self.dtype))
+        if not h.is_contiguous(memory_format=torch.channels_last):
+            h = h.contiguous(memory_format=torch.channels_last)
         for c1, c2 in self.blocks:
             h = c2(c1(h), residual=h)
         if self.kind == "small":

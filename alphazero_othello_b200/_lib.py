@@ -92,8 +92,10 @@ _SIGS = {
     "oth_mcts_begin_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "oth_mcts_step": (C.c_int, [C.c_void_p] * 6),
     "oth_mcts_advance": (C.c_int, [C.c_void_p] * 4),
+    "oth_mcts_poll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "oth_mcts_root_stats": (C.c_int, [C.c_void_p] * 9),
     "oth_unpack_canonical": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "oth_nn_bias_add_relu_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

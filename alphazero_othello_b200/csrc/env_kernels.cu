@@ -288,6 +288,40 @@ __global__ void __launch_bounds__(256) k_symmetry(const int8_t* __restrict__ sta
     }
 }
 
+// Network-boundary epilogue (the network itself stays PyTorch/cuDNN): x = relu(x + bias[c] + res)
+// on channels-last bf16 activations, 8 elements (128 bits) per thread.
+#include <cuda_bf16.h>
+__global__ void __launch_bounds__(256) k_bias_add_relu_bf16(uint4* __restrict__ x, const uint4* __restrict__ res,
+                                                            const __nv_bfloat16* __restrict__ bias, int64_t n8, int C)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        uint4 a = x[i];
+        const uint4 r = res[i];
+        const int c0 = (int)((i * 8) % C);
+        const uint4 bv = *reinterpret_cast<const uint4*>(bias + c0);
+        __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
+        const __nv_bfloat162* pr = reinterpret_cast<const __nv_bfloat162*>(&r);
+        const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&bv);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float2 fa = __bfloat1622float2(pa[k]), fr = __bfloat1622float2(pr[k]), fb = __bfloat1622float2(pb[k]);
+            pa[k] = __floats2bfloat162_rn(fmaxf(fa.x + fb.x + fr.x, 0.0f), fmaxf(fa.y + fb.y + fr.y, 0.0f));
+        }
+        x[i] = a;
+    }
+}
+
+extern "C" int oth_nn_bias_add_relu_bf16(void* x, const void* res, const void* bias, int64_t n, int32_t channels, void* stream)
+{
+    if (n < 0 || channels <= 0 || (channels % 8) || (n % 8) || !x || !res || !bias) return OTH_E_ARG;
+    if ((((uintptr_t)x | (uintptr_t)res | (uintptr_t)bias) & 15) != 0) return OTH_E_ARG;
+    if (n == 0) return OTH_OK;
+    k_bias_add_relu_bf16<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((uint4*)x, (const uint4*)res,
+                                                                                (const __nv_bfloat16*)bias, n / 8, channels);
+    return cuda_status(cudaGetLastError());
+}
+
 // canonical packed boards [n][2] -> int8 [n,64] (+1 own / -1 opp)
 extern "C" int oth_unpack_canonical(const uint64_t* boards, int8_t* states, int64_t n, void* stream)
 {

@@ -859,34 +859,30 @@ struct Ctx {
             int* gp = P.path + (size_t)slot * P.cfg.path_cap;
             for (int d = lane; d < depth; d += LANES) gp[d] = S.path[d];
         }
-        if (c.phase == OTH_PH_ERROR) count(OTH_CNT_ERRORS);
-        if (c.phase == OTH_PH_WAIT_EVAL) count(OTH_CNT_WAITING);
-        if (c.phase == OTH_PH_WAIT_EVAL || c.phase == OTH_PH_RUN) count(OTH_CNT_ACTIVE);
-        count_max(OTH_CNT_MAX_TOP, (unsigned)c.top);
         if (lane == 0) P.ctl[slot] = c;
         tile.sync();
     }
 };
 
-// Per-group counters -> one shared-memory reduction per block -> one global atomic per
-// counter per block.
-__device__ __forceinline__ void flush_counters(unsigned long long* blk, const unsigned* cnt, unsigned long long* global, bool leader)
+// Per-group counters (shared memory, no atomics) -> summed per block by 16 threads -> one
+// global atomic per non-zero counter per block.
+template <int LANES>
+__device__ __forceinline__ void flush_counters(const Scratch* scratch, unsigned long long* global)
 {
-    if (leader) {
-#pragma unroll
-        for (int i = 0; i < CNT_LOCAL; i++) {
-            const unsigned v = cnt[i];
-            if (v == 0) continue;
-            if (i == OTH_CNT_MAX_TOP || i == OTH_CNT_MAX_DEPTH) atomicMax(blk + i, (unsigned long long)v);
-            else atomicAdd(blk + i, (unsigned long long)v);
-        }
-    }
     __syncthreads();
-    if (threadIdx.x < CNT_LOCAL && blk[threadIdx.x]) {
+    if (threadIdx.x < CNT_LOCAL) {
         const int i = threadIdx.x;
-        if (i == OTH_CNT_POSITIONS || i == OTH_CNT_OUT_GAMES) return;  // bumped directly by emit_game
-        if (i == OTH_CNT_MAX_TOP || i == OTH_CNT_MAX_DEPTH) atomicMax(global + i, blk[i]);
-        else atomicAdd(global + i, blk[i]);
+        const bool is_max = (i == OTH_CNT_MAX_TOP || i == OTH_CNT_MAX_DEPTH);
+        unsigned long long v = 0;
+#pragma unroll
+        for (int g = 0; g < kBlock / LANES; g++) {
+            const unsigned x = scratch[g].cnt[i];
+            v = is_max ? (x > v ? x : v) : v + x;
+        }
+        if (v) {
+            if (is_max) atomicMax(global + i, v);
+            else atomicAdd(global + i, v);
+        }
     }
 }
 
@@ -894,9 +890,6 @@ template <int LANES>
 __global__ void __launch_bounds__(kBlock, 7) k_mcts_step(const Params P)
 {
     __shared__ Scratch scratch[kBlock / LANES];
-    __shared__ unsigned long long blk_cnt[CNT_LOCAL];
-    if (threadIdx.x < CNT_LOCAL) blk_cnt[threadIdx.x] = 0;
-    __syncthreads();
     cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
     Ctx<LANES> ctx(tile, P, scratch[threadIdx.x / LANES]);
     const int groups = (gridDim.x * kBlock) / LANES;
@@ -904,7 +897,33 @@ __global__ void __launch_bounds__(kBlock, 7) k_mcts_step(const Params P)
         ctx.slot = s;
         ctx.run_slot();
     }
-    flush_counters(blk_cnt, ctx.S.cnt, P.counters, ctx.lane == 0);
+    flush_counters<LANES>(scratch, P.counters);
+}
+
+// Gauges on demand (not in the hot kernel): slots waiting for the network, slots still playing,
+// slots in error, fullest arena.
+__global__ void k_mcts_poll(const Params P)
+{
+    unsigned waiting = 0, active = 0, errors = 0, top = 0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.cfg.n_slots; s += gridDim.x * blockDim.x) {
+        const int ph = P.ctl[s].phase;
+        waiting += ph == OTH_PH_WAIT_EVAL;
+        active += (ph == OTH_PH_WAIT_EVAL || ph == OTH_PH_RUN);
+        errors += ph == OTH_PH_ERROR || P.ctl[s].error != 0;
+        top = max(top, (unsigned)P.ctl[s].top);
+    }
+    for (int o = 16; o; o >>= 1) {
+        waiting += __shfl_xor_sync(0xffffffffu, waiting, o);
+        active += __shfl_xor_sync(0xffffffffu, active, o);
+        errors += __shfl_xor_sync(0xffffffffu, errors, o);
+        top = max(top, __shfl_xor_sync(0xffffffffu, top, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (waiting) atomicAdd(P.counters + OTH_CNT_WAITING, (unsigned long long)waiting);
+        if (active) atomicAdd(P.counters + OTH_CNT_ACTIVE, (unsigned long long)active);
+        if (errors) atomicAdd(P.counters + OTH_CNT_ERRORS, (unsigned long long)errors);
+        atomicMax(P.counters + OTH_CNT_MAX_TOP, (unsigned long long)top);
+    }
 }
 
 // Start fresh games (self-play) on every slot.
@@ -961,9 +980,6 @@ template <int LANES>
 __global__ void __launch_bounds__(kBlock) k_mcts_advance(const Params P, const int32_t* actions)
 {
     __shared__ Scratch scratch[kBlock / LANES];
-    __shared__ unsigned long long blk_cnt[CNT_LOCAL];
-    if (threadIdx.x < CNT_LOCAL) blk_cnt[threadIdx.x] = 0;
-    __syncthreads();
     cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
     Ctx<LANES> ctx(tile, P, scratch[threadIdx.x / LANES]);
     const int groups = (gridDim.x * kBlock) / LANES;
@@ -995,7 +1011,7 @@ __global__ void __launch_bounds__(kBlock) k_mcts_advance(const Params P, const i
         if (ctx.lane == 0) P.ctl[s] = ctx.c;
         tile.sync();
     }
-    flush_counters(blk_cnt, ctx.S.cnt, P.counters, ctx.lane == 0);
+    flush_counters<LANES>(scratch, P.counters);
 }
 
 template <int LANES>
@@ -1174,10 +1190,20 @@ extern "C" int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers*
     p.priors = priors;
     p.values = values;
     p.nn_input = nn_input;
-    // per-launch gauges
+    LAUNCH_LANES(k_mcts_step, mcts_grid(cfg), stream, p);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int oth_mcts_poll(const oth_mcts_config* cfg, const oth_mcts_buffers* b, void* stream)
+{
+    Params p;
+    const int rc = make_params(cfg, b, &p);
+    if (rc != OTH_OK) return rc;
     int e = cuda_status(cudaMemsetAsync(p.counters + OTH_CNT_WAITING, 0, 2 * 8, (cudaStream_t)stream));
     if (e != OTH_OK) return e;
-    LAUNCH_LANES(k_mcts_step, mcts_grid(cfg), stream, p);
+    e = cuda_status(cudaMemsetAsync(p.counters + OTH_CNT_ERRORS, 0, 2 * 8, (cudaStream_t)stream));  // ERRORS, MAX_TOP
+    if (e != OTH_OK) return e;
+    k_mcts_poll<<<sm_count(), 256, 0, (cudaStream_t)stream>>>(p);
     return cuda_status(cudaGetLastError());
 }
 

@@ -27,7 +27,7 @@ class MctsEngine:
     """
 
     def __init__(self, n_slots, args, *, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=-1,
-                 device="cuda:0", node_cap=None, path_cap=128, max_inline_sims=8, inject_random=False, lanes=32,
+                 device="cuda:0", node_cap=None, path_cap=128, max_inline_sims=8, inject_random=False, lanes=8,
                  seed=0, game_id_base=0, game_id_stride=None, stub_salt=0, out_pos_cap=None, out_game_cap=None):
         _lib.require_device()
         self.device = torch.device(device)
@@ -86,7 +86,10 @@ class MctsEngine:
     def counters_t(self):
         return self._t[_lib.BUF_COUNTERS][:16]
 
-    def counters(self):
+    def counters(self, poll=True):
+        """Event counters (cumulative) + gauges (waiting / active / errors / max_top, refreshed here)."""
+        if poll:
+            self._call(self.L.oth_mcts_poll, self._stream())
         v = self.counters_t.cpu().numpy()
         return {n: int(v[i]) for i, n in enumerate(_lib.CNT_NAMES)}
 

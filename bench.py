@@ -370,7 +370,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--games", type=int, default=0, help="override concurrent games per GPU")
     ap.add_argument("--iters-per-step", type=int, default=0)
-    ap.add_argument("--lanes", type=int, default=32)
+    ap.add_argument("--lanes", type=int, default=8)
     ap.add_argument("--max-inline", type=int, default=8)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")

@@ -212,13 +212,13 @@ enum {
     OTH_CNT_POSITIONS,    /* replay tuples emitted since the last drain */
     OTH_CNT_OUT_GAMES,    /* finished-game descriptors since the last drain */
     OTH_CNT_MOVES,        /* moves played */
-    OTH_CNT_ERRORS,       /* slots that entered OTH_PH_ERROR */
-    OTH_CNT_MAX_TOP,      /* largest arena fill seen */
+    OTH_CNT_ERRORS,       /* slots in error (gauge, oth_mcts_poll) */
+    OTH_CNT_MAX_TOP,      /* fullest arena (gauge, oth_mcts_poll) */
     OTH_CNT_MAX_DEPTH,    /* deepest path seen */
     OTH_CNT_NODES,        /* nodes created */
     OTH_CNT_COPIED,       /* nodes copied by re-rooting */
-    OTH_CNT_WAITING,      /* slots in OTH_PH_WAIT_EVAL after the last launch */
-    OTH_CNT_ACTIVE,       /* slots not DONE/IDLE/ERROR after the last launch */
+    OTH_CNT_WAITING,      /* slots in OTH_PH_WAIT_EVAL (gauge, oth_mcts_poll) */
+    OTH_CNT_ACTIVE,       /* slots not DONE/IDLE/ERROR (gauge, oth_mcts_poll) */
     OTH_CNT_LEVELS,       /* tree levels descended (select steps) */
     OTH_CNT_CHILDREN      /* child records scanned by select */
 };
@@ -253,6 +253,10 @@ int oth_mcts_begin_search(const oth_mcts_config* cfg, const oth_mcts_buffers* b,
 int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const float* priors, const float* values,
                   float* nn_input, void* stream);
 
+/* Refresh the gauges OTH_CNT_WAITING / ACTIVE / ERRORS / MAX_TOP from the slots' control blocks
+ * (kept out of the hot kernel; hosts call this when they want to know whether to stop). */
+int oth_mcts_poll(const oth_mcts_config* cfg, const oth_mcts_buffers* b, void* stream);
+
 /* Manual mode: MCTS.make_move (MCTS_model.py:200-215) on every slot;
  * actions[slot] < 0 leaves that slot alone. */
 int oth_mcts_advance(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const int32_t* actions, void* stream);
@@ -265,6 +269,12 @@ int oth_mcts_root_stats(const oth_mcts_config* cfg, const oth_mcts_buffers* b, i
 /* Replay tuples -> the reference's array form: int8 [n,64] canonical states
  * (state*player, self_play_worker.py:72) from packed boards. */
 int oth_unpack_canonical(const uint64_t* boards /* [n][2] own,opp */, int8_t* states, int64_t n, void* stream);
+
+/* Network boundary helper (the policy/value network itself stays PyTorch, Models.py):
+ * in-place x = relu(x + bias[channel] + res) on channels-last bf16 activations -- the residual
+ * epilogue of ResidualBlock.forward (Models.py:81-89) after BatchNorm folding.
+ * n = element count (multiple of 8), channels multiple of 8, 16-byte aligned pointers. */
+int oth_nn_bias_add_relu_bf16(void* x, const void* res, const void* bias, int64_t n, int32_t channels, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,14 +11,18 @@ fname, line, text, hdr = "", "", "", None
 agg = defaultdict(lambda: defaultdict(float))
 src = {}
 kernel = 0
+seen_files = set()
 for r in rows:
     if not r:
         continue
     if r[0] == "Kernel Name":
-        kernel += 1
         continue
-    if r[0] == "File Name":
+    if r[0] in ("File Name", "File Path"):
         fname = r[1].split("/")[-1]
+        if fname in seen_files:  # the dump repeats every file once per profiled launch: keep the first
+            kernel = 2
+        elif kernel < 2:
+            seen_files.add(fname)
         continue
     if r[0] == "Line No":
         hdr = r
@@ -41,6 +45,29 @@ for r in rows:
                      "stall_branch_resolving", "stall_not_selected", "stall_selected", "stall_no_inst", "stall_dispatch"):
             if name in hdr:
                 agg[k][name] += num(r[hdr.index(name)])
+import os
+import re
+by_fn = "--functions" in sys.argv
+if by_fn:  # roll lines up to the enclosing __device__ function of the repo's sources
+    regions = {}
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in ("mcts_kernels.cu", "bitboard.cuh", "philox.cuh", "env_kernels.cu"):
+        path = os.path.join(here, "alphazero_othello_b200", "csrc", f)
+        regions[f] = [(i, m.group(1)) for i, l in enumerate(open(path), 1)
+                      for m in [re.match(r"\s*(?:template.*>\s*)?(?:static\s+)?__(?:device|global)__ .*?(\w+)\(", l)] if m]
+    def region(k):
+        f, ln = k
+        name = f
+        for start, n in regions.get(f, []):
+            if ln.isdigit() and int(ln) >= start:
+                name = f + ":" + n
+        return name
+    rolled = defaultdict(lambda: defaultdict(float))
+    for k, v in agg.items():
+        for n, x in v.items():
+            rolled[(region(k), "")][n] += x
+    agg = rolled
+    src = {}
 tot = sum(v["samples"] for v in agg.values())
 toti = sum(v["inst"] for v in agg.values())
 print(f"total samples {tot:.0f}, warp instructions {toti:.0f}")
