@@ -124,12 +124,21 @@ struct __align__(16) Scratch {
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// sm_100a warp-reduce units: float max and integer min over the lanes named by `mask`
+__device__ __forceinline__ float redux_max_f32(float v, unsigned mask)
+{
+    float m;
+    asm volatile("redux.sync.max.f32 %0, %1, %2;" : "=f"(m) : "f"(v), "r"(mask));
+    return m;
+}
+
 template <int LANES>
 struct Ctx {
     cg::thread_block_tile<LANES> tile;
     const Params& P;
     Scratch& S;
     int lane;
+    unsigned gmask;  // lanes of this group within the warp
     int slot;
     Node* N;        // current arena
     ulonglong2* B;
@@ -137,6 +146,7 @@ struct Ctx {
 
     __device__ Ctx(cg::thread_block_tile<LANES> t, const Params& p, Scratch& s) : tile(t), P(p), S(s), lane(t.thread_rank()), slot(0)
     {
+        gmask = LANES == 32 ? 0xffffffffu : (((1u << (LANES & 31)) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
         for (int i = lane; i < CNT_LOCAL; i += LANES) S.cnt[i] = 0;
         tile.sync();
     }
@@ -298,7 +308,7 @@ struct Ctx {
     // create every child in ascending action order (Node.expand :146-158,
     // Node.__init__ :68-108 -- child boards, legal sets and terminal values
     // are computed here, one child per lane).
-    __device__ bool expand(int leaf, bool root_init, const Node& lf, const ulonglong2 lb)
+    __device__ bool expand(int leaf, bool root_init, const Node& lf, const ulonglong2 lb, bool premasked)
     {
         const u64 own = lb.x, opp = lb.y;
         const u64 M = lf.moves;
@@ -310,6 +320,7 @@ struct Ctx {
             return false;
         }
         const bool f64 = root_init && P.cfg.dirichlet_epsilon > 0.0;
+        float sum32 = 0.0f;
         if (f64) {
             make_noise();
             const double* nz = P.noise + (size_t)slot * OTH_NUM_ACTIONS;
@@ -327,15 +338,14 @@ struct Ctx {
             if (s > 1e-12)
                 for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri64[a] = __ddiv_rn(S.pri64[a], s);
         } else {
-            for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) {
-                const bool valid = a < 64 ? ((M >> a) & 1) : is_pass;
-                if (!valid) S.pri[a] = __fmul_rn(S.pri[a], 0.0f);
+            if (!premasked) {
+                for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) {
+                    const bool valid = a < 64 ? ((M >> a) & 1) : is_pass;
+                    if (!valid) S.pri[a] = __fmul_rn(S.pri[a], 0.0f);
+                }
+                tile.sync();
             }
-            tile.sync();
-            const float s = np_sum65_f32();
-            tile.sync();
-            if (s > (float)1e-12)
-                for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri[a] = __fdiv_rn(S.pri[a], s);
+            sum32 = np_sum65_f32();  // the division (priors /= sum, :348-349) is applied per child below
         }
         tile.sync();
         for (int i = lane; i < nchild; i += LANES) {
@@ -354,7 +364,7 @@ struct Ctx {
                 P.root_prior64[(size_t)slot * OTH_MAX_CHILDREN + i] = S.pri64[a];
                 ch.prior = (float)S.pri64[a];
             } else {
-                ch.prior = S.pri[a];
+                ch.prior = sum32 > (float)1e-12 ? __fdiv_rn(S.pri[a], sum32) : S.pri[a];
             }
             store_node(N + fc + i, ch);
             B[fc + i] = make_ulonglong2(cb.own, cb.opp);
@@ -412,49 +422,59 @@ struct Ctx {
             const double sq = sqrt((double)(nd.N + 1) + 1e-8);
             const float sq32 = (float)sq;
             const bool f64 = (depth == 1) && (c.flags & 2);
-            double bs = -INFINITY;
             int bi = 0x7fffffff;
             int k_N = 0, k_fc = -1;
             uint32_t k_meta = 0;
-            u64 k_moves = 0;
-            for (int i = lane; i < nchild; i += LANES) {
-                const Node ch = load_node(N + fc + i);
-                const double q = ch.N ? -__ddiv_rn(ch.W, (double)ch.N) : -0.0;
-                double sc;
-                if (!f64) {
+            if (!f64) {
+                float bs = -INFINITY;
+                for (int i = lane; i < nchild; i += LANES) {
+                    const Node ch = load_node(N + fc + i);
+                    const double q = ch.N ? -__ddiv_rn(ch.W, (double)ch.N) : -0.0;
                     float u = __fmul_rn(cp32, ch.prior);
                     u = __fmul_rn(u, sq32);
                     u = __fdiv_rn(u, (float)(1 + ch.N));
-                    sc = (double)__fadd_rn((float)q, u);
-                } else {
+                    const float sc = __fadd_rn((float)q, u);
+                    if (sc > bs) {  // ascending i: the first maximum wins (:366-369)
+                        bs = sc;
+                        bi = i;
+                        k_N = ch.N;
+                        k_fc = ch.first_child;
+                        k_meta = ch.meta;
+                    }
+                }
+                const float m = redux_max_f32(bs, gmask);
+                bi = (int)__reduce_min_sync(gmask, (unsigned)((bs == m) ? bi : 0x7fffffff));
+            } else {
+                double bs = -INFINITY;
+                for (int i = lane; i < nchild; i += LANES) {
+                    const Node ch = load_node(N + fc + i);
+                    const double q = ch.N ? -__ddiv_rn(ch.W, (double)ch.N) : -0.0;
                     double u = __dmul_rn(cp64, P.root_prior64[(size_t)slot * OTH_MAX_CHILDREN + i]);
                     u = __dmul_rn(u, sq);
                     u = __ddiv_rn(u, (double)(1 + ch.N));
-                    sc = __dadd_rn(q, u);
+                    const double sc = __dadd_rn(q, u);
+                    if (sc > bs) {
+                        bs = sc;
+                        bi = i;
+                        k_N = ch.N;
+                        k_fc = ch.first_child;
+                        k_meta = ch.meta;
+                    }
                 }
-                if (sc > bs) {  // ascending i: the first maximum wins (:366-369)
-                    bs = sc;
-                    bi = i;
-                    k_N = ch.N;
-                    k_fc = ch.first_child;
-                    k_meta = ch.meta;
-                    k_moves = ch.moves;
-                }
-            }
 #pragma unroll
-            for (int o = LANES / 2; o; o >>= 1) {
-                const double os = tile.shfl_xor(bs, o);
-                const int oi = tile.shfl_xor(bi, o);
-                if (os > bs || (os == bs && oi < bi)) {
-                    bs = os;
-                    bi = oi;
+                for (int o = LANES / 2; o; o >>= 1) {
+                    const double os = tile.shfl_xor(bs, o);
+                    const int oi = tile.shfl_xor(bi, o);
+                    if (os > bs || (os == bs && oi < bi)) {
+                        bs = os;
+                        bi = oi;
+                    }
                 }
             }
             const int src = bi & (LANES - 1);
             nd.N = tile.shfl(k_N, src);
             nd.first_child = tile.shfl(k_fc, src);
             nd.meta = tile.shfl(k_meta, src);
-            nd.moves = tile.shfl(k_moves, src);
             cur = fc + bi;
             // the chosen child's board is needed only if it turns out to be the leaf: start fetching it now
             prefetch_l2(B + cur);
@@ -792,13 +812,14 @@ struct Ctx {
                 for (int i = lane; i < rn; i += LANES) prefetch_l2(N + rfc + i);
             }
 #pragma unroll
-            for (int k = 0; k < NPL; k++) {
+            for (int k = 0; k < NPL; k++) {  // priors *= valid_mask (:346) fused into the staging store
                 const int a = lane + k * LANES;
-                if (a < OTH_NUM_ACTIONS) S.pri[a] = pv[k];
+                const bool valid = a < 64 ? ((lf.moves >> a) & 1) : (lf.moves == 0);
+                if (a < OTH_NUM_ACTIONS) S.pri[a] = valid ? pv[k] : __fmul_rn(pv[k], 0.0f);
             }
             tile.sync();
             const bool root_init = c.flags & 1;
-            if (expand(c.pending, root_init, lf, lb)) {
+            if (expand(c.pending, root_init, lf, lb, true)) {
                 backup(c.path_len, (double)nn_value);
                 if (!root_init) {
                     c.sims_done++;
@@ -838,8 +859,8 @@ struct Ctx {
             const ulonglong2 lb = B[leaf];
             if (stub) {
                 const double value = eval_stub(lb.x, lb.y);
-                nd.first_child = -1;
-                if (!expand(leaf, root_init, nd, lb)) break;
+                const Node lf = load_node(N + leaf);
+                if (!expand(leaf, root_init, lf, lb, false)) break;
                 backup(depth, value);
                 if (!root_init) {
                     c.sims_done++;
