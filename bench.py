@@ -159,7 +159,8 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     desc, kind, G, sims = WORKLOADS[a.workload]
     if a.games:
         G = a.games
@@ -237,6 +238,7 @@ def run_b200(a):
     clk = clocks.stop()
     eng.raise_on_error()
     sims_total = total(d["sims"])
+    moves_total = total(d["moves"])
     value = sims_total / (ms * 1e-3)
     eng.drain(to_host=False)
 
@@ -306,7 +308,7 @@ def run_b200(a):
                        "iters_per_step": iters, "lanes": a.lanes, "cuda_graph": not a.no_graph,
                        "l2": f"tree arenas {eng.buf_bytes[0] + eng.buf_bytes[1] >> 20} MiB per GPU >> 126 MB L2 (inputs larger than L2)",
                        "sharding": "games by id, no collective on the search path"},
-            "positions_per_s": total(d["moves"]) / (ms * 1e-3),
+            "positions_per_s": moves_total / (ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": "sims/s", "h2d_bytes_per_step": io["h2d"] // a.steps,
                     "d2h_bytes_per_step": io["d2h"] // a.steps, "ms_per_step": ms2 / a.steps,
                     "includes": "weights H2D from pinned host (+NCCL broadcast if sharded), BN re-fold, "
@@ -322,6 +324,7 @@ def run_b200(a):
         }
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
     return out, dev
 
 
