@@ -118,7 +118,7 @@ enum { CNT_LOCAL = 16 };
 struct __align__(16) Scratch {
     double pri64[OTH_NUM_ACTIONS + 1];
     float pri[OTH_NUM_ACTIONS + 3];
-    int path[256];
+    int path[128];
     unsigned cnt[CNT_LOCAL];  // per-group event counters (lane 0 only), flushed once per launch
 };
 
@@ -148,7 +148,20 @@ struct Ctx {
     {
         gmask = LANES == 32 ? 0xffffffffu : (((1u << (LANES & 31)) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
         for (int i = lane; i < CNT_LOCAL; i += LANES) S.cnt[i] = 0;
-        tile.sync();
+        gsync();
+    }
+
+    // group collectives on the precomputed lane mask (cheaper than the cooperative-groups tile wrappers)
+    __device__ __forceinline__ void gsync() const { __syncwarp(gmask); }
+    template <typename T>
+    __device__ __forceinline__ T gshfl(T v, int src) const { return __shfl_sync(gmask, v, src, LANES); }
+    template <typename T>
+    __device__ __forceinline__ T gshfl_xor(T v, int m) const { return __shfl_xor_sync(gmask, v, m, LANES); }
+    template <typename T>
+    __device__ __forceinline__ T gshfl_up(T v, int d) const { return __shfl_up_sync(gmask, v, d, LANES); }
+    __device__ __forceinline__ unsigned gballot(bool p) const
+    {
+        return LANES == 32 ? __ballot_sync(gmask, p) : ((__ballot_sync(gmask, p) & gmask) >> ((threadIdx.x & 31) & ~(LANES - 1)));
     }
 
     __device__ __forceinline__ void count(int which, unsigned n = 1)
@@ -182,10 +195,10 @@ struct Ctx {
 #pragma unroll
             for (int i = 1; i < 8; i++) r = __fadd_rn(r, S.pri[8 * i + lane]);
         }
-        r = __fadd_rn(r, tile.shfl_xor(r, 1));
-        r = __fadd_rn(r, tile.shfl_xor(r, 2));
-        r = __fadd_rn(r, tile.shfl_xor(r, 4));
-        r = tile.shfl(r, 0);
+        r = __fadd_rn(r, gshfl_xor(r, 1));
+        r = __fadd_rn(r, gshfl_xor(r, 2));
+        r = __fadd_rn(r, gshfl_xor(r, 4));
+        r = gshfl(r, 0);
         return __fadd_rn(r, S.pri[64]);
     }
 
@@ -197,10 +210,10 @@ struct Ctx {
 #pragma unroll
             for (int i = 1; i < 8; i++) r = __dadd_rn(r, S.pri64[8 * i + lane]);
         }
-        r = __dadd_rn(r, tile.shfl_xor(r, 1));
-        r = __dadd_rn(r, tile.shfl_xor(r, 2));
-        r = __dadd_rn(r, tile.shfl_xor(r, 4));
-        r = tile.shfl(r, 0);
+        r = __dadd_rn(r, gshfl_xor(r, 1));
+        r = __dadd_rn(r, gshfl_xor(r, 2));
+        r = __dadd_rn(r, gshfl_xor(r, 4));
+        r = gshfl(r, 0);
         return __dadd_rn(r, S.pri64[64]);
     }
 
@@ -233,7 +246,7 @@ struct Ctx {
         } else if (kind == OTH_EVAL_STUB_B) {
             long long h = 0;
             for (int e = lane; e < 64; e += LANES) h += ((own >> e) & 1) ? (e + 1) : (((opp >> e) & 1) ? -(e + 1) : 0);
-            for (int o = LANES / 2; o; o >>= 1) h += tile.shfl_xor(h, o);
+            for (int o = LANES / 2; o; o >>= 1) h += gshfl_xor(h, o);
             float sum = 0.0f;  // small integers: exact in any order
             for (int a = 0; a < OTH_NUM_ACTIONS; a++) {
                 long long t = (7LL * a + h) % 11;
@@ -252,14 +265,14 @@ struct Ctx {
             const u64 h = mix64(__brevll(own) ^ mix64(__brevll(opp) ^ P.cfg.stub_salt));
             int part = 0;
             for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) part += 1 + (int)(mix64(h + (u64)a) % 251ULL);
-            for (int o = LANES / 2; o; o >>= 1) part += tile.shfl_xor(part, o);
+            for (int o = LANES / 2; o; o >>= 1) part += gshfl_xor(part, o);
             const float sum = (float)part;
             for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES)
                 S.pri[a] = __fdiv_rn((float)(1 + (int)(mix64(h + (u64)a) % 251ULL)), sum);
             const int v = (int)(mix64(h ^ 0x9e3779b97f4a7c15ULL) % 2001ULL) - 1000;
             value = (double)__fdiv_rn((float)v, 1000.0f);
         }
-        tile.sync();
+        gsync();
         return value;
     }
 
@@ -293,12 +306,12 @@ struct Ctx {
                 }
                 S.pri64[e] = g;
             }
-            tile.sync();
+            gsync();
             double s = 0.0;
             for (int e = 0; e < OTH_NUM_ACTIONS; e++) s += S.pri64[e];
-            tile.sync();
+            gsync();
             for (int e = lane; e < OTH_NUM_ACTIONS; e += LANES) nz[e] = S.pri64[e] / s;
-            tile.sync();
+            gsync();
         }
     }
 
@@ -332,9 +345,9 @@ struct Ctx {
                 const bool valid = a < 64 ? ((M >> a) & 1) : is_pass;
                 S.pri64[a] = valid ? v : __dmul_rn(v, 0.0);
             }
-            tile.sync();
+            gsync();
             const double s = np_sum65_f64();
-            tile.sync();
+            gsync();
             if (s > 1e-12)
                 for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri64[a] = __ddiv_rn(S.pri64[a], s);
         } else {
@@ -343,11 +356,11 @@ struct Ctx {
                     const bool valid = a < 64 ? ((M >> a) & 1) : is_pass;
                     if (!valid) S.pri[a] = __fmul_rn(S.pri[a], 0.0f);
                 }
-                tile.sync();
+                gsync();
             }
             sum32 = np_sum65_f32();  // the division (priors /= sum, :348-349) is applied per child below
         }
-        tile.sync();
+        gsync();
         for (int i = lane; i < nchild; i += LANES) {
             const int a = is_pass ? OTH_PASS : nth_set_bit(M, i);
             const u64 f = is_pass ? 0ULL : flips(own, opp, 1ULL << a);
@@ -380,21 +393,21 @@ struct Ctx {
             c.reserved = (long long)(unsigned)fc | ((long long)nchild << 32);
         }
         count(OTH_CNT_NODES, nchild);
-        tile.sync();
+        gsync();
         return true;
     }
 
     // Node.backpropagate (MCTS_model.py:160-169) along S.path[0..depth).
     __device__ __forceinline__ void backup(int depth, double value)
     {
-        tile.sync();
+        gsync();
         for (int d = lane; d < depth; d += LANES) {
             Node* p = N + S.path[d];
             const double sv = ((depth - 1 - d) & 1) ? -value : value;
             p->N += 1;
             p->W = __dadd_rn(p->W, sv);
         }
-        tile.sync();
+        gsync();
     }
 
     // MCTS._simulate's descent (MCTS_model.py:372-392) with _select_child /
@@ -463,8 +476,8 @@ struct Ctx {
                 }
 #pragma unroll
                 for (int o = LANES / 2; o; o >>= 1) {
-                    const double os = tile.shfl_xor(bs, o);
-                    const int oi = tile.shfl_xor(bi, o);
+                    const double os = gshfl_xor(bs, o);
+                    const int oi = gshfl_xor(bi, o);
                     if (os > bs || (os == bs && oi < bi)) {
                         bs = os;
                         bi = oi;
@@ -472,9 +485,9 @@ struct Ctx {
                 }
             }
             const int src = bi & (LANES - 1);
-            nd.N = tile.shfl(k_N, src);
-            nd.first_child = tile.shfl(k_fc, src);
-            nd.meta = tile.shfl(k_meta, src);
+            nd.N = gshfl(k_N, src);
+            nd.first_child = gshfl(k_fc, src);
+            nd.meta = gshfl(k_meta, src);
             cur = fc + bi;
             // the chosen child's board is needed only if it turns out to be the leaf: start fetching it now
             prefetch_l2(B + cur);
@@ -509,7 +522,7 @@ struct Ctx {
         c.flags = 0;
         c.reserved = -1;
         c.phase = OTH_PH_RUN;
-        tile.sync();
+        gsync();
     }
 
     // ---------------------------------------------------------- re-root --
@@ -529,7 +542,7 @@ struct Ctx {
             store_node(Nd, r);
             Bd[0] = Bs[new_root];
         }
-        tile.sync();
+        gsync();
         int top = 1, i = 0;
         while (i < top) {
             const int chunk = min(LANES, top - i);
@@ -542,17 +555,17 @@ struct Ctx {
             int incl = nch;
 #pragma unroll
             for (int o = 1; o < LANES; o <<= 1) {
-                const int t = tile.shfl_up(incl, o);
+                const int t = gshfl_up(incl, o);
                 if (lane >= o) incl += t;
             }
             const int excl = incl - nch;
-            const int total = tile.shfl(incl, LANES - 1);
+            const int total = gshfl(incl, LANES - 1);
             if (lane < chunk && nch > 0) Nd[i + lane].first_child = top + excl;
-            unsigned pm = tile.ballot(nch > 0);
+            unsigned pm = gballot(nch > 0);
             while (pm) {
                 const int l = __ffs(pm) - 1;
                 pm &= pm - 1;
-                const int o_ = tile.shfl(ofc, l), n_ = tile.shfl(nch, l), d_ = top + tile.shfl(excl, l);
+                const int o_ = gshfl(ofc, l), n_ = gshfl(nch, l), d_ = top + gshfl(excl, l);
                 for (int j = lane; j < n_; j += LANES) {
                     const uint4* s = reinterpret_cast<const uint4*>(Ns + o_ + j);
                     uint4* d = reinterpret_cast<uint4*>(Nd + d_ + j);
@@ -565,7 +578,7 @@ struct Ctx {
             }
             top += total;
             i += chunk;
-            tile.sync();
+            gsync();
         }
         count(OTH_CNT_COPIED, top);
         c.root = 0;
@@ -583,12 +596,12 @@ struct Ctx {
     {
         const int fc = root.first_child, nchild = meta_nchild(root.meta);
         for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri[a] = 0.0f;
-        tile.sync();
+        gsync();
         for (int i = lane; i < nchild; i += LANES) {
             const Node ch = load_node(N + fc + i);
             S.pri[meta_action(ch.meta)] = (float)ch.N;
         }
-        tile.sync();
+        gsync();
         if (fabs(temp) < 1e-1) {
             if (lane == 0) {
                 float mx = S.pri[0];
@@ -605,20 +618,20 @@ struct Ctx {
                     }
                 for (int a = 0; a < OTH_NUM_ACTIONS; a++) S.pri[a] = (a == pick) ? 1.0f : 0.0f;
             }
-            tile.sync();
+            gsync();
             return;
         }
         if (temp != 1.0) {
             const float ex = (float)(1.0 / temp);
             for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri[a] = powf(S.pri[a], ex);
-            tile.sync();
+            gsync();
         }
         const float norm = np_sum65_f32();
-        tile.sync();
+        gsync();
         if (norm < (float)1e-12) {  // all-zero counts: uniform over valid actions (:260-269)
             const int nv = max(1, nchild);
             for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri[a] = 0.0f;
-            tile.sync();
+            gsync();
             for (int i = lane; i < nchild; i += LANES) {
                 const Node ch = load_node(N + fc + i);
                 S.pri[meta_action(ch.meta)] = (float)(1.0 / (double)nv);
@@ -626,7 +639,7 @@ struct Ctx {
         } else {
             for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri[a] = __fdiv_rn(S.pri[a], norm);
         }
-        tile.sync();
+        gsync();
     }
 
     // np.random.choice(65, p) given its uniform (self_play_worker.py:75)
@@ -642,7 +655,7 @@ struct Ctx {
                 if (__ddiv_rn(acc, last) <= u) act = a + 1;
             }
         }
-        return tile.shfl(act, 0);
+        return gshfl(act, 0);
     }
 
     __device__ double uniform_for(uint32_t purpose, int ply)
@@ -660,8 +673,8 @@ struct Ctx {
             base = (long long)atomicAdd(P.counters + OTH_CNT_POSITIONS, (unsigned long long)nply);
             gi = (long long)atomicAdd(P.counters + OTH_CNT_OUT_GAMES, 1ULL);
         }
-        base = tile.shfl(base, 0);
-        gi = tile.shfl(gi, 0);
+        base = gshfl(base, 0);
+        gi = gshfl(gi, 0);
         if (base + nply > P.cfg.out_pos_cap || gi >= P.cfg.out_game_cap) {
             fail(OTH_ERR_OUT_OVERFLOW);
             return;
@@ -746,15 +759,15 @@ struct Ctx {
                 cmeta = b.y;
             }
         }
-        const unsigned hit = tile.ballot(ci >= 0);
+        const unsigned hit = gballot(ci >= 0);
         if (!hit) {
             fail(OTH_ERR_BAD_ACTION);
             return;
         }
         const int src = __ffs(hit) - 1;
-        ci = tile.shfl(ci, src);
-        cmeta = tile.shfl(cmeta, src);
-        tile.sync();
+        ci = gshfl(ci, src);
+        cmeta = gshfl(cmeta, src);
+        gsync();
         if (meta_flags(cmeta) & kFlagTerminal) {
             // reward is read from the mover's side (:78-82); the child's terminal value is the opponent's
             const int reward = -meta_tvalue(cmeta);
@@ -817,7 +830,7 @@ struct Ctx {
                 const bool valid = a < 64 ? ((lf.moves >> a) & 1) : (lf.moves == 0);
                 if (a < OTH_NUM_ACTIONS) S.pri[a] = valid ? pv[k] : __fmul_rn(pv[k], 0.0f);
             }
-            tile.sync();
+            gsync();
             const bool root_init = c.flags & 1;
             if (expand(c.pending, root_init, lf, lb, true)) {
                 backup(c.path_len, (double)nn_value);
@@ -876,12 +889,12 @@ struct Ctx {
             c.flags = (c.flags & ~1) | (root_init ? 1 : 0);
             c.phase = OTH_PH_WAIT_EVAL;
             write_nn_input(lb.x, lb.y);
-            tile.sync();
+            gsync();
             int* gp = P.path + (size_t)slot * P.cfg.path_cap;
             for (int d = lane; d < depth; d += LANES) gp[d] = S.path[d];
         }
         if (lane == 0) P.ctl[slot] = c;
-        tile.sync();
+        gsync();
     }
 };
 
@@ -908,7 +921,7 @@ __device__ __forceinline__ void flush_counters(const Scratch* scratch, unsigned 
 }
 
 template <int LANES>
-__global__ void __launch_bounds__(kBlock, 7) k_mcts_step(const Params P)
+__global__ void __launch_bounds__(kBlock, 8) k_mcts_step(const Params P)
 {
     __shared__ Scratch scratch[kBlock / LANES];
     cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
@@ -1078,7 +1091,7 @@ __global__ void __launch_bounds__(kBlock) k_mcts_root_stats(const Params P, int3
 int check_cfg(const oth_mcts_config* cfg)
 {
     if (!cfg) return OTH_E_ARG;
-    if (cfg->n_slots <= 0 || cfg->node_cap < 64 || cfg->path_cap < 2 || cfg->path_cap > 256) return OTH_E_ARG;
+    if (cfg->n_slots <= 0 || cfg->node_cap < 64 || cfg->path_cap < 2 || cfg->path_cap > 128) return OTH_E_ARG;
     if (cfg->num_simulations < 0 || cfg->max_inline_sims <= 0) return OTH_E_ARG;
     if (cfg->lanes != 8 && cfg->lanes != 16 && cfg->lanes != 32) return OTH_E_ARG;
     if (cfg->eval_kind < OTH_EVAL_EXTERNAL || cfg->eval_kind > OTH_EVAL_STUB_H) return OTH_E_ARG;

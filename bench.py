@@ -295,6 +295,10 @@ def run_b200(a):
     alg = algorithmic_bytes(dk, G, iters) / iters
     peak, peak_src = measured_peaks()
     achieved = alg / (k_avg * 1e-3) / 1e9
+    traffic = None  # dram__bytes_read+write per launch from the committed `ncu --set full` capture of this config
+    prof = os.path.join(ROOT, "profiles", f"r01_mcts_step_{a.workload}_l{a.lanes}.json")
+    if os.path.exists(prof) and not a.games:
+        traffic = json.load(open(prof)).get("dram_bytes_per_launch")
     eng.drain(to_host=False)
 
     out = None
@@ -316,8 +320,9 @@ def run_b200(a):
             "gpu_launches": a.steps * iters,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": f"k_mcts_step<{a.lanes}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg, "launch_ms_avg": k_avg, "launch_ms_median": kms[len(kms) // 2],
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg, "launch_ms_avg": k_avg, "launch_ms_median": kms[len(kms) // 2], "launch_ms_max": kms[-1],
+                         "launch_ms_p90": kms[int(len(kms) * 0.9)],
                          "bytes_per_sim": algorithmic_bytes(dk, G, iters) / max(dk["sims"], 1),
                          "kernel_share_of_iteration": k_avg / (ms / a.steps / iters)},
             "search_counters_per_step": {k: d[k] / a.steps for k in ("sims", "evals", "terminal_sims", "moves", "games", "nodes", "copied", "levels", "children")},
@@ -362,6 +367,37 @@ def aux_env(dev):
             "int32_roofline": {"bound": "int32-alu", "instr_per_ply": 600, "achieved_ginstr_s": steps_s * 600 / 1e9,
                                "peak_ginstr_s": ips.value / 1e9, "frac": steps_s * 600 / ips.value,
                                "peak_source": "measured live: LOP3+IADD3 probe kernel (oth_host_int32_peak)"}}
+
+
+def aux_search_only(dev, G, sims, lanes):
+    """Search-only variant: the same kernel with the device hash-stub evaluator, so a
+    launch runs whole simulations back to back without the network in between."""
+    import torch
+    from alphazero_othello_b200 import _lib
+    from alphazero_othello_b200.engine import MctsEngine
+    args = dict(TRAIN_ARGS, num_simulations=sims)
+    eng = MctsEngine(G, args, self_play=True, eval_kind=_lib.EVAL_STUB_H, games_per_slot=-1, device=dev, lanes=lanes,
+                     max_inline_sims=16, out_pos_cap=G * 80, out_game_cap=G + 64, stub_salt=1)
+    eng.reset()
+    for _ in range(30):
+        eng.step()
+    eng.drain(to_host=False)
+    c0 = eng.counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 60
+    for _ in range(n):
+        eng.step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    c1 = eng.counters()
+    ms = e0.elapsed_time(e1)
+    d = {k: c1[k] - c0[k] for k in c1}
+    eng.raise_on_error()
+    peak, _ = measured_peaks()
+    gbs = algorithmic_bytes(dict(d, evals=0), G, n) / (ms * 1e-3) / 1e9  # no network I/O in this variant
+    return {"workload": f"search-only: {G} games, {sims} sims/move, device stub evaluator, 16 simulations per slot per launch",
+            "sims_per_s": d["sims"] / (ms * 1e-3), "launch_ms": ms / n, "hbm_gbs": gbs, "hbm_frac": gbs / peak}
 
 
 def main():
@@ -409,6 +445,7 @@ def main():
     if rank == 0:
         if world == 1 and not a.no_aux:
             out["aux"] = aux_env(dev)
+            out["aux"]["search_only"] = aux_search_only(dev, out["config"]["games_per_gpu"], sims, a.lanes)
         if world == 1 and not a.no_cpu_baseline:
             import oracle
             oracle.build()

@@ -138,7 +138,7 @@ int oth_host_int32_peak(double* out_ips, float* kernel_ms);
 typedef struct oth_mcts_config {
     int32_t n_slots;          /* concurrent games on this GPU */
     int32_t node_cap;         /* nodes per arena per slot (two arenas per slot) */
-    int32_t path_cap;         /* max search depth (<= 256) */
+    int32_t path_cap;         /* max search depth (<= 128) */
     int32_t num_simulations;  /* args["num_simulations"], MCTS_model.py:237 */
     int32_t num_exploratory_moves; /* self_play_worker.py:66-67 */
     int32_t eval_kind;        /* OTH_EVAL_* */
