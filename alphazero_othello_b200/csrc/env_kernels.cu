@@ -348,6 +348,68 @@ __global__ void __launch_bounds__(256) k_int32_probe(unsigned* __restrict__ out,
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
 }
 
+// Random-access HBM probe: every thread reads `per_thread` pseudo-random, independent chunks of
+// `chunk` bytes (32/64/128) from a buffer much larger than L2 -- the access pattern of tree
+// records -- so the MCTS kernel can be judged against what HBM delivers for that pattern.
+__global__ void __launch_bounds__(256) k_random_read_probe(const uint4* __restrict__ buf, uint64_t n_chunks, int chunk16, int per_thread,
+                                                           unsigned* __restrict__ sink)
+{
+    uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ULL + 0x1234567ULL;
+    unsigned acc = 0;
+    for (int k = 0; k < per_thread; k += 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {  // 4 independent requests in flight per thread
+            x ^= x >> 29;
+            x *= 0xBF58476D1CE4E5B9ULL;
+            x ^= x >> 32;
+            const uint64_t c = x % n_chunks;
+            v[u] = buf[c * chunk16];
+            for (int q = 1; q < chunk16; q++) {
+                const uint4 w = buf[c * chunk16 + q];
+                v[u].x ^= w.x ^ w.y ^ w.z ^ w.w;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+    }
+    if (acc == 0x7fffffff) sink[0] = acc;
+}
+
+extern "C" int oth_host_random_read_probe(int64_t buffer_bytes, int32_t chunk_bytes, double* out_gbs, float* kernel_ms)
+{
+    if (buffer_bytes < (1 << 20) || (chunk_bytes != 32 && chunk_bytes != 64 && chunk_bytes != 128)) return OTH_E_ARG;
+    void *buf = nullptr, *sink = nullptr;
+    int rc = cuda_status(cudaMalloc(&buf, (size_t)buffer_bytes));
+    if (rc != OTH_OK) return rc;
+    cudaMalloc(&sink, 64);
+    cudaMemset(buf, 1, (size_t)buffer_bytes);
+    const int blocks = sm_count() * 8, threads = 256, per_thread = 64;
+    const uint64_t n_chunks = (uint64_t)buffer_bytes / chunk_bytes;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, 0);
+        k_random_read_probe<<<blocks, threads>>>((const uint4*)buf, n_chunks, chunk_bytes / 16, per_thread, (unsigned*)sink);
+        cudaEventRecord(e1, 0);
+        cudaStreamSynchronize(0);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    rc = cuda_status(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    cudaFree(sink);
+    if (rc != OTH_OK) return rc;
+    if (out_gbs) *out_gbs = (double)blocks * threads * per_thread * chunk_bytes / (best * 1e-3) / 1e9;
+    if (kernel_ms) *kernel_ms = best;
+    return OTH_OK;
+}
+
 // ----------------------------------------------------------------- C ABI --
 
 static char g_cuda_err[256] = "";

@@ -106,6 +106,7 @@ struct Params {
     long long* out_meta;
     long long* out_games;
     unsigned long long* counters;
+    unsigned* slot_counters;  // [slot][16] cumulative event counters, summed by k_mcts_poll
     const float* priors;
     const float* values;
     float* nn_input;
@@ -119,7 +120,7 @@ struct __align__(16) Scratch {
     double pri64[OTH_NUM_ACTIONS + 1];
     float pri[OTH_NUM_ACTIONS + 3];
     int path[128];
-    unsigned cnt[CNT_LOCAL];  // per-group event counters (lane 0 only), flushed once per launch
+    unsigned cnt[CNT_LOCAL];  // the slot's cumulative event counters while it is being worked on
 };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -147,8 +148,17 @@ struct Ctx {
     __device__ Ctx(cg::thread_block_tile<LANES> t, const Params& p, Scratch& s) : tile(t), P(p), S(s), lane(t.thread_rank()), slot(0)
     {
         gmask = LANES == 32 ? 0xffffffffu : (((1u << (LANES & 31)) - 1u) << ((threadIdx.x & 31) & ~(LANES - 1)));
-        for (int i = lane; i < CNT_LOCAL; i += LANES) S.cnt[i] = 0;
+    }
+
+    // per-slot event counters live in HBM next to the control block: no atomics, no block barrier
+    __device__ __forceinline__ void load_counters()
+    {
+        for (int i = lane; i < CNT_LOCAL; i += LANES) S.cnt[i] = P.slot_counters[(size_t)slot * CNT_LOCAL + i];
+    }
+    __device__ __forceinline__ void store_counters()
+    {
         gsync();
+        for (int i = lane; i < CNT_LOCAL; i += LANES) P.slot_counters[(size_t)slot * CNT_LOCAL + i] = S.cnt[i];
     }
 
     // group collectives on the precomputed lane mask (cheaper than the cooperative-groups tile wrappers)
@@ -807,8 +817,10 @@ struct Ctx {
             }
             nn_value = P.values[slot];
         }
+        load_counters();
         c = P.ctl[slot];
         bind_arena();
+        gsync();
         if (c.phase == OTH_PH_WAIT_EVAL) {
             // (2) second round trip: leaf record + board, the path, and L2 prefetches of what
             //     backup and the next descent will touch (path nodes, root, root's children)
@@ -894,31 +906,10 @@ struct Ctx {
             for (int d = lane; d < depth; d += LANES) gp[d] = S.path[d];
         }
         if (lane == 0) P.ctl[slot] = c;
+        store_counters();
         gsync();
     }
 };
-
-// Per-group counters (shared memory, no atomics) -> summed per block by 16 threads -> one
-// global atomic per non-zero counter per block.
-template <int LANES>
-__device__ __forceinline__ void flush_counters(const Scratch* scratch, unsigned long long* global)
-{
-    __syncthreads();
-    if (threadIdx.x < CNT_LOCAL) {
-        const int i = threadIdx.x;
-        const bool is_max = (i == OTH_CNT_MAX_TOP || i == OTH_CNT_MAX_DEPTH);
-        unsigned long long v = 0;
-#pragma unroll
-        for (int g = 0; g < kBlock / LANES; g++) {
-            const unsigned x = scratch[g].cnt[i];
-            v = is_max ? (x > v ? x : v) : v + x;
-        }
-        if (v) {
-            if (is_max) atomicMax(global + i, v);
-            else atomicAdd(global + i, v);
-        }
-    }
-}
 
 template <int LANES>
 __global__ void __launch_bounds__(kBlock, 8) k_mcts_step(const Params P)
@@ -931,32 +922,38 @@ __global__ void __launch_bounds__(kBlock, 8) k_mcts_step(const Params P)
         ctx.slot = s;
         ctx.run_slot();
     }
-    flush_counters<LANES>(scratch, P.counters);
 }
 
-// Gauges on demand (not in the hot kernel): slots waiting for the network, slots still playing,
-// slots in error, fullest arena.
-__global__ void k_mcts_poll(const Params P)
+// Counters on demand (kept out of the hot kernel): sums the per-slot event counters and derives
+// the gauges (slots waiting for the network, slots still playing, slots in error, fullest arena)
+// from the control blocks.  POSITIONS / OUT_GAMES are live atomics of emit_game and left alone.
+__global__ void __launch_bounds__(256) k_mcts_poll(const Params P)
 {
-    unsigned waiting = 0, active = 0, errors = 0, top = 0;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.cfg.n_slots; s += gridDim.x * blockDim.x) {
-        const int ph = P.ctl[s].phase;
-        waiting += ph == OTH_PH_WAIT_EVAL;
-        active += (ph == OTH_PH_WAIT_EVAL || ph == OTH_PH_RUN);
-        errors += ph == OTH_PH_ERROR || P.ctl[s].error != 0;
-        top = max(top, (unsigned)P.ctl[s].top);
+    __shared__ unsigned long long acc[CNT_LOCAL];
+    if (threadIdx.x < CNT_LOCAL) acc[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = threadIdx.x & (CNT_LOCAL - 1);
+    const bool is_max = (i == OTH_CNT_MAX_TOP || i == OTH_CNT_MAX_DEPTH);
+    unsigned long long v = 0;
+    // 16 consecutive threads read one slot's 16 counters (64 B)
+    for (long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / CNT_LOCAL; s < P.cfg.n_slots;
+         s += ((long long)gridDim.x * blockDim.x) / CNT_LOCAL) {
+        unsigned x = P.slot_counters[s * CNT_LOCAL + i];
+        const oth_mcts_ctl* c = P.ctl + s;
+        if (i == OTH_CNT_WAITING) x = c->phase == OTH_PH_WAIT_EVAL;
+        if (i == OTH_CNT_ACTIVE) x = (c->phase == OTH_PH_WAIT_EVAL || c->phase == OTH_PH_RUN);
+        if (i == OTH_CNT_ERRORS) x = (c->phase == OTH_PH_ERROR || c->error != 0);
+        if (i == OTH_CNT_MAX_TOP) x = (unsigned)c->top;
+        v = is_max ? (x > v ? x : v) : v + x;
     }
-    for (int o = 16; o; o >>= 1) {
-        waiting += __shfl_xor_sync(0xffffffffu, waiting, o);
-        active += __shfl_xor_sync(0xffffffffu, active, o);
-        errors += __shfl_xor_sync(0xffffffffu, errors, o);
-        top = max(top, __shfl_xor_sync(0xffffffffu, top, o));
+    if (v) {
+        if (is_max) atomicMax(acc + i, v);
+        else atomicAdd(acc + i, v);
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (waiting) atomicAdd(P.counters + OTH_CNT_WAITING, (unsigned long long)waiting);
-        if (active) atomicAdd(P.counters + OTH_CNT_ACTIVE, (unsigned long long)active);
-        if (errors) atomicAdd(P.counters + OTH_CNT_ERRORS, (unsigned long long)errors);
-        atomicMax(P.counters + OTH_CNT_MAX_TOP, (unsigned long long)top);
+    __syncthreads();
+    if (threadIdx.x < CNT_LOCAL && acc[threadIdx.x] && i != OTH_CNT_POSITIONS && i != OTH_CNT_OUT_GAMES) {
+        if (is_max) atomicMax(P.counters + i, acc[i]);
+        else atomicAdd(P.counters + i, acc[i]);
     }
 }
 
@@ -976,6 +973,7 @@ __global__ void __launch_bounds__(kBlock) k_mcts_reset(const Params P)
         ctx.c.games_left = P.cfg.games_per_slot < 0 ? -1 : P.cfg.games_per_slot;
         ctx.init_tree(INIT_BLACK, INIT_WHITE, 1);
         if (P.cfg.games_per_slot == 0) ctx.c.phase = OTH_PH_DONE;
+        for (int i = ctx.lane; i < CNT_LOCAL; i += LANES) P.slot_counters[(size_t)s * CNT_LOCAL + i] = 0;
         if (ctx.lane == 0) P.ctl[s] = ctx.c;
     }
 }
@@ -995,6 +993,7 @@ __global__ void __launch_bounds__(kBlock) k_mcts_set_roots(const Params P, const
         ctx.c.games_left = -1;
         ctx.init_tree(own[s], opp[s], players[s]);
         ctx.c.phase = OTH_PH_IDLE;
+        for (int i = ctx.lane; i < CNT_LOCAL; i += LANES) P.slot_counters[(size_t)s * CNT_LOCAL + i] = 0;
         if (ctx.lane == 0) P.ctl[s] = ctx.c;
     }
 }
@@ -1023,7 +1022,9 @@ __global__ void __launch_bounds__(kBlock) k_mcts_advance(const Params P, const i
         ctx.slot = s;
         ctx.c = P.ctl[s];
         if (ctx.c.phase == OTH_PH_ERROR) continue;
+        ctx.load_counters();
         ctx.bind_arena();
+        tile.sync();
         const Node root = load_node(ctx.N + ctx.c.root);
         const int fc = root.first_child, nchild = root.first_child < 0 ? 0 : meta_nchild(root.meta);
         int ci = -1;
@@ -1043,9 +1044,9 @@ __global__ void __launch_bounds__(kBlock) k_mcts_advance(const Params P, const i
             ctx.c.phase = OTH_PH_IDLE;
         }
         if (ctx.lane == 0) P.ctl[s] = ctx.c;
+        ctx.store_counters();
         tile.sync();
     }
-    flush_counters<LANES>(scratch, P.counters);
 }
 
 template <int LANES>
@@ -1129,6 +1130,7 @@ int make_params(const oth_mcts_config* cfg, const oth_mcts_buffers* b, Params* p
     p->out_meta = (long long*)b->buf[OTH_BUF_OUT_META];
     p->out_games = (long long*)b->buf[OTH_BUF_OUT_GAMES];
     p->counters = (unsigned long long*)b->buf[OTH_BUF_COUNTERS];
+    p->slot_counters = (unsigned*)b->buf[OTH_BUF_SLOT_COUNTERS];
     p->priors = nullptr;
     p->values = nullptr;
     p->nn_input = nullptr;
@@ -1178,6 +1180,7 @@ extern "C" int oth_mcts_buffer_bytes(const oth_mcts_config* cfg, int64_t* out)
     out[OTH_BUF_OUT_META] = sp ? cfg->out_pos_cap * 8 : 0;
     out[OTH_BUF_OUT_GAMES] = sp ? cfg->out_game_cap * 32 : 0;
     out[OTH_BUF_COUNTERS] = 16 * 8;
+    out[OTH_BUF_SLOT_COUNTERS] = G * CNT_LOCAL * 4;
     return OTH_OK;
 }
 
@@ -1233,9 +1236,10 @@ extern "C" int oth_mcts_poll(const oth_mcts_config* cfg, const oth_mcts_buffers*
     Params p;
     const int rc = make_params(cfg, b, &p);
     if (rc != OTH_OK) return rc;
-    int e = cuda_status(cudaMemsetAsync(p.counters + OTH_CNT_WAITING, 0, 2 * 8, (cudaStream_t)stream));
+    // everything except the two live output-ring counters is re-derived
+    int e = cuda_status(cudaMemsetAsync(p.counters, 0, OTH_CNT_POSITIONS * 8, (cudaStream_t)stream));
     if (e != OTH_OK) return e;
-    e = cuda_status(cudaMemsetAsync(p.counters + OTH_CNT_ERRORS, 0, 2 * 8, (cudaStream_t)stream));  // ERRORS, MAX_TOP
+    e = cuda_status(cudaMemsetAsync(p.counters + OTH_CNT_MOVES, 0, (16 - OTH_CNT_MOVES) * 8, (cudaStream_t)stream));
     if (e != OTH_OK) return e;
     k_mcts_poll<<<sm_count(), 256, 0, (cudaStream_t)stream>>>(p);
     return cuda_status(cudaGetLastError());

@@ -295,6 +295,13 @@ def run_b200(a):
     alg = algorithmic_bytes(dk, G, iters) / iters
     peak, peak_src = measured_peaks()
     achieved = alg / (k_avg * 1e-3) / 1e9
+    # what HBM delivers for the tree's access pattern: independent random 64-byte reads over a
+    # footprint the size of the arenas (row-activation / TLB bound, far below the streaming copy peak)
+    import ctypes as C
+    rnd_gbs, rnd_ms = C.c_double(0), C.c_float(0)
+    foot = min(max(eng.buf_bytes[0] + eng.buf_bytes[1], 1 << 30), 24 << 30)
+    if _lib.lib().oth_host_random_read_probe(foot, 64, C.byref(rnd_gbs), C.byref(rnd_ms)) != 0:
+        rnd_gbs.value = 0.0
     traffic = None  # dram__bytes_read+write per launch from the committed `ncu --set full` capture of this config
     prof = os.path.join(ROOT, "profiles", f"r01_mcts_step_{a.workload}_l{a.lanes}.json")
     if os.path.exists(prof) and not a.games:
@@ -324,6 +331,8 @@ def run_b200(a):
                          "algorithmic_bytes_per_launch": alg, "launch_ms_avg": k_avg, "launch_ms_median": kms[len(kms) // 2], "launch_ms_max": kms[-1],
                          "launch_ms_p90": kms[int(len(kms) * 0.9)],
                          "bytes_per_sim": algorithmic_bytes(dk, G, iters) / max(dk["sims"], 1),
+                         "random_access": {"peak": rnd_gbs.value, "unit": "GB/s", "frac": achieved / rnd_gbs.value if rnd_gbs.value else None,
+                                           "how": f"measured live: independent random 64-byte reads over {foot >> 20} MiB (oth_host_random_read_probe)"},
                          "kernel_share_of_iteration": k_avg / (ms / a.steps / iters)},
             "search_counters_per_step": {k: d[k] / a.steps for k in ("sims", "evals", "terminal_sims", "moves", "games", "nodes", "copied", "levels", "children")},
         }

@@ -113,6 +113,10 @@ int oth_host_rollout(uint64_t seed, uint64_t game_id_base, int64_t n_games, int3
  * measured thread-instructions per second in *out_ips. */
 int oth_host_int32_peak(double* out_ips, float* kernel_ms);
 
+/* Random-access HBM probe: independent pseudo-random reads of chunk_bytes (32, 64 or 128) from a
+ * buffer_bytes buffer (>> L2), the access pattern of tree records; GB/s in *out_gbs. */
+int oth_host_random_read_probe(int64_t buffer_bytes, int32_t chunk_bytes, double* out_gbs, float* kernel_ms);
+
 /* ----------------------------------------------------------------- MCTS -- */
 
 /* evaluator kinds */
@@ -200,7 +204,8 @@ enum {
     OTH_BUF_OUT_VALUE,   /* double [out_pos_cap]  value target G_t */
     OTH_BUF_OUT_META,    /* int64 [out_pos_cap]: game_id << 16 | ply << 8 | (player & 0xff) */
     OTH_BUF_OUT_GAMES,   /* int64 [out_game_cap][4]: game_id, first position, n positions, winner */
-    OTH_BUF_COUNTERS,    /* uint64 [16], see OTH_CNT_* */
+    OTH_BUF_COUNTERS,    /* uint64 [16], see OTH_CNT_*: refreshed by oth_mcts_poll */
+    OTH_BUF_SLOT_COUNTERS, /* uint32 [slot][16] cumulative per-slot event counters */
     OTH_BUF_COUNT
 };
 
@@ -253,8 +258,9 @@ int oth_mcts_begin_search(const oth_mcts_config* cfg, const oth_mcts_buffers* b,
 int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const float* priors, const float* values,
                   float* nn_input, void* stream);
 
-/* Refresh the gauges OTH_CNT_WAITING / ACTIVE / ERRORS / MAX_TOP from the slots' control blocks
- * (kept out of the hot kernel; hosts call this when they want to know whether to stop). */
+/* Refresh OTH_BUF_COUNTERS: sums the per-slot event counters and derives the gauges (WAITING /
+ * ACTIVE / ERRORS / MAX_TOP) from the control blocks.  Kept out of the hot kernel; hosts call
+ * it when they want totals or need to know whether to stop. */
 int oth_mcts_poll(const oth_mcts_config* cfg, const oth_mcts_buffers* b, void* stream);
 
 /* Manual mode: MCTS.make_move (MCTS_model.py:200-215) on every slot;
