@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libothello_b200.so")
-SOURCES = ["env_kernels.cu", "mcts_kernels.cu"]
+SOURCES = ["env_kernels.cu", "mcts_kernels.cu", "replay_kernels.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -198,6 +198,29 @@ class BatchedOthello:
                                               n_trace, ta.data_ptr(), tm.data_ptr(), cnt.data_ptr(), self._stream()))
         return dict(score=score, plies=plies, final=final, trace_actions=ta[:n_trace], trace_moves=tm[:n_trace], counters=cnt)
 
+    def symmetry(self, states, pis, ks, flips):
+        """Training-time augmentation on device (RandomSymmetryDataset.__getitem__, train.py:36-42,
+        batched): states int8[n,8,8], pis f32[n,65], ks int32[n] quarter turns, flips uint8[n].
+        Returns (float32 [n,1,8,8], float32 [n,65]) exactly as get_random_symmetry would per sample."""
+        t = self.torch
+        n = states.shape[0]
+        states, pis = states.contiguous(), pis.contiguous()
+        ks, flips = ks.to(t.int32).contiguous(), flips.to(t.uint8).contiguous()
+        os_ = t.empty((n, 1, 8, 8), dtype=t.float32, device=self.device)
+        op = t.empty((n, 65), dtype=t.float32, device=self.device)
+        with t.cuda.device(self.device):
+            _lib.check(_lib.lib().oth_symmetry(states.data_ptr(), pis.data_ptr(), ks.data_ptr(), flips.data_ptr(), os_.data_ptr(),
+                                               op.data_ptr(), n, self._stream()))
+        return os_, op
+
+    def random_symmetry(self, states, pis, generator=None):
+        """One random dihedral image per sample (k ~ U{0..3}, flip ~ Bernoulli(1/2)), drawn on the device."""
+        t = self.torch
+        n = states.shape[0]
+        ks = t.randint(0, 4, (n,), device=self.device, dtype=t.int32, generator=generator)
+        flips = (t.rand(n, device=self.device, generator=generator) < 0.5).to(t.uint8)
+        return self.symmetry(states, pis, ks, flips)
+
     def pack(self, states, players):
         t = self.torch
         n = states.shape[0]

@@ -1,0 +1,65 @@
+"""Replay-buffer ingest on the GPU: the caller of the self-play path.
+
+``aggregate_duplicates`` is ``Trainer._aggregate_duplicates`` (train.py:142-173) as one CUDA
+pipeline over packed replay tuples -- the form ``MctsEngine.drain`` already produces -- instead
+of a Python dict keyed by sha1 hashes.  ``to_training_arrays`` gives the float32 arrays
+``Trainer.setup_dataloader`` (train.py:175-197) builds from it.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def aggregate_duplicates(boards, pis, values, versions, device="cuda:0"):
+    """boards int64[n,2] (own, opp canonical), pis f32[n,65], values f64[n], versions int32[n]
+    (torch tensors, host or device).  Returns dict(boards int64[m,2], pis f32[m,65],
+    values f32[m], versions int32[m], counts int32[m]) on the device, in first-occurrence order."""
+    _lib.require_device()
+    dev = torch.device(device)
+    boards = boards.to(dev, torch.int64).contiguous()
+    pis = pis.to(dev, torch.float32).contiguous()
+    values = values.to(dev, torch.float64).contiguous()
+    versions = versions.to(dev, torch.int32).contiguous()
+    n = int(values.numel())
+    assert boards.shape == (n, 2) and pis.shape == (n, 65) and versions.numel() == n
+    L = _lib.lib()
+    nb = C.c_int64(0)
+    _lib.check(L.oth_replay_aggregate_workspace_bytes(n, C.byref(nb)))
+    ws = torch.empty(max(nb.value, 8), dtype=torch.uint8, device=dev)
+    ob = torch.empty((max(n, 1), 2), dtype=torch.int64, device=dev)
+    op = torch.empty((max(n, 1), 65), dtype=torch.float32, device=dev)
+    ov = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    over = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    oc = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    om = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.oth_replay_aggregate(boards.data_ptr(), pis.data_ptr(), values.data_ptr(), versions.data_ptr(), n,
+                                          ws.data_ptr(), ws.numel(), ob.data_ptr(), op.data_ptr(), ov.data_ptr(), over.data_ptr(),
+                                          oc.data_ptr(), om.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                   "oth_replay_aggregate")
+    m = int(om.item())
+    return dict(boards=ob[:m], pis=op[:m], values=ov[:m], versions=over[:m], counts=oc[:m])
+
+
+def to_training_arrays(agg):
+    """(states f32[m,8,8], policies f32[m,65], values f32[m,1]) as train.py:184-186 builds them."""
+    m = agg["values"].numel()
+    dev = agg["values"].device
+    states = torch.empty((m, 8, 8), dtype=torch.int8, device=dev)
+    if m:
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().oth_unpack_canonical(agg["boards"].contiguous().data_ptr(), states.data_ptr(), m,
+                                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return states.float(), agg["pis"], agg["values"].reshape(-1, 1)
+
+
+def pack_states(states):
+    """int8 canonical boards [n,8,8] (numpy) -> int64[n,2] (own, opp), bit i = row*8+col."""
+    s = np.asarray(states).reshape(len(states), 64)
+    w = (np.uint64(1) << np.arange(64, dtype=np.uint64))
+    own = ((s == 1) * w).sum(1, dtype=np.uint64)
+    opp = ((s == -1) * w).sum(1, dtype=np.uint64)
+    return torch.from_numpy(np.stack([own, opp], 1).view(np.int64))

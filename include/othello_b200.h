@@ -276,6 +276,19 @@ int oth_mcts_root_stats(const oth_mcts_config* cfg, const oth_mcts_buffers* b, i
  * (state*player, self_play_worker.py:72) from packed boards. */
 int oth_unpack_canonical(const uint64_t* boards /* [n][2] own,opp */, int8_t* states, int64_t n, void* stream);
 
+/* ------------------------------------------------------- replay ingest -- */
+
+/* Trainer._aggregate_duplicates (train.py:142-173) on the GPU: collapse replay tuples with the
+ * same (canonical board, model version) into one sample -- mean policy re-normalised, mean value
+ * -- in order of first occurrence.  Inputs: boards uint64[n][2] (own, opp), pis float32[n][65],
+ * values float64[n], versions int32[n] (n < 2^31).  Outputs are sized n; *out_m (device int64)
+ * receives the number of unique samples; out_counts their multiplicities.  workspace: device
+ * scratch of oth_replay_aggregate_workspace_bytes(n) bytes. */
+int oth_replay_aggregate_workspace_bytes(int64_t n, int64_t* bytes);
+int oth_replay_aggregate(const uint64_t* boards, const float* pis, const double* values, const int32_t* versions, int64_t n,
+                         void* workspace, int64_t workspace_bytes, uint64_t* out_boards, float* out_pis, float* out_values,
+                         int32_t* out_versions, int32_t* out_counts, int64_t* out_m, void* stream);
+
 /* Network boundary helper (the policy/value network itself stays PyTorch, Models.py):
  * in-place x = relu(x + bias[channel] + res) on channels-last bf16 activations -- the residual
  * epilogue of ResidualBlock.forward (Models.py:81-89) after BatchNorm folding.

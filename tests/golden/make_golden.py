@@ -364,10 +364,45 @@ def gen_selfplay():
     OUT["sp_cases"] = np.array(names)
 
 
+# ---------------------------------------------------------- replay ingest ---
+def gen_replay():
+    """Trainer._aggregate_duplicates (train.py:142-173) run on a replay buffer built from the
+    self-play fixtures above (shared openings => real duplicates), via the unbound method."""
+    import collections
+    import train as ref_train
+
+    class FakeTrainer:
+        _hash_state = ref_train.Trainer._hash_state
+
+    buf = []
+    order = [("sp0", 0), ("sp1", 1), ("sp2", 0), ("sp3", 1), ("sp0", 0), ("sp2", 1)]
+    for name, ver in order:
+        pre = f"sp_{name}_"
+        for s, pi, v in zip(OUT[pre + "states"], OUT[pre + "pis"], OUT[pre + "values"]):
+            buf.append((s.astype(np.int8), pi.astype(np.float32).copy(), float(v), ver))
+    t = FakeTrainer()
+    t.replay_buffer = collections.deque(buf)
+    states, policies, values = ref_train.Trainer._aggregate_duplicates(t)
+    OUT["rp_in_states"] = np.stack([b[0] for b in buf]).astype(np.int8)
+    OUT["rp_in_pis"] = np.stack([b[1] for b in buf]).astype(np.float32)
+    OUT["rp_in_values"] = np.array([b[2] for b in buf], np.float64)
+    OUT["rp_in_versions"] = np.array([b[3] for b in buf], np.int32)
+    OUT["rp_out_states"] = np.stack(states).astype(np.int8)
+    OUT["rp_out_pis"] = np.stack(policies).astype(np.float32)
+    OUT["rp_out_values"] = np.array(values, np.float32)
+    print("replay", len(buf), "->", len(states), "unique")
+
+
 if __name__ == "__main__":
-    gen_env()
-    gen_mcts()
-    gen_selfplay()
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_golden.npz")
+    if "--update" in sys.argv:  # keep existing fixtures, (re)generate only the named groups
+        OUT.update(np.load(dst))
+        for g in sys.argv[sys.argv.index("--update") + 1:]:
+            globals()["gen_" + g]()
+    else:
+        gen_env()
+        gen_mcts()
+        gen_selfplay()
+        gen_replay()
     np.savez_compressed(dst, **OUT)
     print("wrote", dst, os.path.getsize(dst), "bytes")

@@ -199,3 +199,29 @@ def test_device_step_and_legal_moves_vs_oracle():
 def test_empty_batches(game):
     assert game.valid_moves_batch(np.zeros((0, 8, 8), np.int8), np.zeros(0, np.int8)).shape == (0, 65)
     assert game.next_state_batch(np.zeros((0, 8, 8), np.int8), np.zeros(0, np.int32), np.zeros(0, np.int8)).shape == (0, 8, 8)
+
+
+def test_device_symmetry_batch_vs_oracle():
+    import torch
+    import oracle as O
+    from alphazero_othello_b200.envs.othello import BatchedOthello
+    env = BatchedOthello()
+    rs = np.random.RandomState(2)
+    n = 4097
+    S = rs.randint(-1, 2, size=(n, 8, 8)).astype(np.int8)
+    P = rs.rand(n, 65).astype(np.float32)
+    ks = rs.randint(0, 4, n).astype(np.int32)
+    fl = (rs.rand(n) < 0.5).astype(np.uint8)
+    s2, p2 = env.symmetry(torch.from_numpy(S).cuda(), torch.from_numpy(P).cuda(), torch.from_numpy(ks).cuda(), torch.from_numpy(fl).cuda())
+    s2, p2 = s2.cpu().numpy(), p2.cpu().numpy()
+    assert s2.shape == (n, 1, 8, 8) and s2.dtype == np.float32
+    for i in rs.choice(n, 300, replace=False):
+        rs_, rp = O.symmetry(S[i], P[i], ks[i], fl[i])
+        assert np.array_equal(s2[i], rs_) and np.array_equal(p2[i], rp)
+    # identity and involution properties on the whole batch
+    z = torch.zeros(n, dtype=torch.int32, device="cuda")
+    s0, p0 = env.symmetry(torch.from_numpy(S).cuda(), torch.from_numpy(P).cuda(), z, z.to(torch.uint8))
+    assert np.array_equal(s0.cpu().numpy()[:, 0], S.astype(np.float32)) and np.array_equal(p0.cpu().numpy(), P)
+    r1, q1 = env.random_symmetry(torch.from_numpy(S).cuda(), torch.from_numpy(P).cuda())
+    assert torch.equal(r1.abs().sum((1, 2, 3)), torch.from_numpy(np.abs(S).sum((1, 2)).astype(np.float32)).cuda())
+    assert torch.allclose(q1.sum(1), torch.from_numpy(P.sum(1)).cuda(), atol=1e-4)

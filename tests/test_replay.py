@@ -1,0 +1,73 @@
+"""Replay ingest: duplicate aggregation, train.py:142-173.
+CPU: the numpy oracle against the reference's own output.  GPU: the CUDA pipeline against the
+reference's output (bit-exact) and against the oracle on a large synthetic buffer."""
+import numpy as np
+import pytest
+
+from oracle import replay as OR
+
+
+def _buffer(golden):
+    return [(s, p.copy(), float(v), int(ver)) for s, p, v, ver in zip(golden["rp_in_states"], golden["rp_in_pis"],
+                                                                     golden["rp_in_values"], golden["rp_in_versions"])]
+
+
+def test_oracle_matches_reference(golden):
+    states, policies, values, counts, vers = OR.aggregate_duplicates(_buffer(golden))
+    assert np.array_equal(np.stack(states), golden["rp_out_states"])
+    assert np.array_equal(np.stack(policies), golden["rp_out_pis"])
+    assert np.array_equal(np.array(values, np.float32), golden["rp_out_values"])
+    assert sum(counts) == len(golden["rp_in_values"]) and max(counts) >= 3
+
+
+@pytest.mark.gpu
+def test_gpu_matches_reference_bit_exact(golden):
+    import torch
+    from alphazero_othello_b200 import replay
+    agg = replay.aggregate_duplicates(replay.pack_states(golden["rp_in_states"]), torch.from_numpy(golden["rp_in_pis"]),
+                                      torch.from_numpy(golden["rp_in_values"]), torch.from_numpy(golden["rp_in_versions"]))
+    states, policies, values = replay.to_training_arrays(agg)
+    assert states.dtype == torch.float32 and values.shape == (len(golden["rp_out_values"]), 1)
+    assert np.array_equal(states.cpu().numpy().astype(np.int8), golden["rp_out_states"])
+    assert np.array_equal(policies.cpu().numpy(), golden["rp_out_pis"])
+    assert np.array_equal(values.cpu().numpy().ravel(), golden["rp_out_values"])
+    assert int(agg["counts"].sum()) == len(golden["rp_in_values"])
+
+
+@pytest.mark.gpu
+def test_gpu_matches_oracle_on_large_buffer_with_heavy_duplication():
+    import torch
+    from alphazero_othello_b200 import replay
+    rs = np.random.RandomState(3)
+    uniq = rs.randint(-1, 2, size=(700, 8, 8)).astype(np.int8)
+    n = 40000
+    which = np.minimum((rs.pareto(0.8, n) * 3).astype(np.int64), 699)  # a few very hot states, long tail
+    states = uniq[which]
+    pis = rs.rand(n, 65).astype(np.float32)
+    pis /= pis.sum(1, keepdims=True)
+    values = rs.uniform(-1, 1, n)
+    vers = rs.randint(0, 3, n).astype(np.int32)
+    ref = OR.aggregate_duplicates([(s, p.copy(), float(v), int(k)) for s, p, v, k in zip(states, pis, values, vers)])
+    agg = replay.aggregate_duplicates(replay.pack_states(states), torch.from_numpy(pis), torch.from_numpy(values), torch.from_numpy(vers))
+    st, po, va = replay.to_training_arrays(agg)
+    assert len(ref[0]) == st.shape[0]
+    assert np.array_equal(st.cpu().numpy().astype(np.int8), np.stack(ref[0]))
+    assert np.array_equal(po.cpu().numpy(), np.stack(ref[1]))
+    assert np.array_equal(va.cpu().numpy().ravel(), np.array(ref[2], np.float32))
+    assert np.array_equal(agg["counts"].cpu().numpy(), np.array(ref[3])) and np.array_equal(agg["versions"].cpu().numpy(), np.array(ref[4]))
+    assert max(ref[3]) > 1000  # the hot bucket is walked sequentially, in buffer order
+
+
+@pytest.mark.gpu
+def test_gpu_empty_and_singleton():
+    import torch
+    from alphazero_othello_b200 import replay
+    e = replay.aggregate_duplicates(torch.zeros((0, 2), dtype=torch.int64), torch.zeros((0, 65)), torch.zeros(0, dtype=torch.float64),
+                                    torch.zeros(0, dtype=torch.int32))
+    assert e["values"].numel() == 0
+    pi = torch.rand(1, 65)
+    one = replay.aggregate_duplicates(torch.tensor([[5, 9]]), pi, torch.tensor([0.25], dtype=torch.float64), torch.tensor([4], dtype=torch.int32))
+    assert one["counts"].tolist() == [1] and one["versions"].tolist() == [4] and one["boards"].tolist() == [[5, 9]]
+    p = pi[0].numpy().copy()
+    p = (p / np.float32(1)) ; p /= p.sum() + 1e-12
+    assert np.array_equal(one["pis"].cpu().numpy()[0], p.astype(np.float32))
