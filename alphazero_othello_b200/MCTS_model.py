@@ -12,8 +12,9 @@ the reference's own numpy expressions (:244-274).
 ``policy`` is either a torch module ``policy(x[B,1,8,8]) -> (logits, value)`` (evaluated on
 the GPU straight from the engine's leaf batch) or any object with
 ``inference(state, player) -> (priors f32[65], value)`` (called on the host per leaf).
-``policy=None`` (random-rollout evaluation, MCTS_model.py:276-303) is not part of the
-accelerated path yet.
+``policy=None`` selects the reference's rollout mode (uniform priors + one random playout per
+leaf, MCTS_model.py:276-303, 332-335) evaluated in-kernel; its playouts draw from the engine's
+Philox streams (keyed by ``seed``), not from ``np.random``.
 """
 import numpy as np
 import torch
@@ -46,10 +47,9 @@ class _Root:
 
 class MCTS:
     def __init__(self, env, args, policy, apply_symmetry=False, dirichlet_alpha=0.03, dirichlet_epsilon=0.0,
-                 inference_cache=None, device="cuda:0"):
-        if policy is None:
-            raise NotImplementedError("policy=None (rollout MCTS) is not on the accelerated path yet")
+                 inference_cache=None, device="cuda:0", seed=0):
         self.env, self.args, self.policy = env, args, policy
+        self.use_rollout = policy is None
         self.num_actions = env.action_size
         # apply_symmetry / inference_cache are accepted and ignored: dead code in every reference caller
         self.apply_symmetry, self.inference_cache = apply_symmetry, inference_cache
@@ -58,8 +58,8 @@ class MCTS:
         self.device = torch.device(device)
         eargs = dict(args)
         eargs.update(dirichlet_alpha=dirichlet_alpha, dirichlet_epsilon=dirichlet_epsilon)
-        self._e = MctsEngine(1, eargs, self_play=False, eval_kind=_lib.EVAL_EXTERNAL, inject_random=True,
-                             device=device, max_inline_sims=64)
+        self._e = MctsEngine(1, eargs, self_play=False, eval_kind=_lib.EVAL_ROLLOUT if self.use_rollout else _lib.EVAL_EXTERNAL,
+                             inject_random=True, device=device, max_inline_sims=64, seed=seed)
         self._module = isinstance(policy, torch.nn.Module)
         if self._module:
             self.policy = policy.to(self.device).eval()

@@ -16,7 +16,7 @@ OTH_MAX_CHILDREN = 40
 OTH_OK, OTH_E_CUDA, OTH_E_ARG, OTH_E_ILLEGAL, OTH_E_NO_DEVICE = 0, -1, -2, -3, -4
 F_ILLEGAL, F_TERMINAL, F_WIN, F_LOSS, F_MUST_PASS = 1, 2, 4, 8, 16
 
-EVAL_EXTERNAL, EVAL_STUB_A, EVAL_STUB_B, EVAL_STUB_H = 0, 1, 2, 3
+EVAL_EXTERNAL, EVAL_STUB_A, EVAL_STUB_B, EVAL_STUB_H, EVAL_ROLLOUT = 0, 1, 2, 3, 4
 PH_RUN, PH_WAIT_EVAL, PH_IDLE, PH_DONE, PH_ERROR = 0, 1, 2, 3, 4
 ERR_NAMES = {1: "node arena overflow", 2: "path overflow", 4: "output ring overflow", 8: "ply overflow",
              16: "action has no child (KeyError)"}

@@ -33,6 +33,7 @@ namespace {
 constexpr int kBlock = 128;
 constexpr uint64_t kSaltNoise = 0x6e6f697365ULL;  // Philox purposes
 constexpr uint32_t kPurposeMove = 1, kPurposeTie = 2;
+constexpr uint64_t kSaltRollout = 0x726f6c6c6f7574ULL;
 
 struct __align__(32) Node {
     double W;             // value_sum (MCTS_model.py:84), float64
@@ -243,6 +244,52 @@ struct Ctx {
         x *= 0xc4ceb9fe1a85ec53ULL;
         x ^= x >> 33;
         return x;
+    }
+
+    // policy=None evaluation (MCTS_model.py:332-335): uniform priors np.ones(65) and the outcome of
+    // one uniform-random playout from the leaf, seen from the leaf's side to move (_rollout
+    // :276-303).  Draws come from Philox keyed (seed, game id, ply/root flag, simulation index,
+    // 4 plies per block); move choice = floor(u32 * n_legal / 2^32)-th legal action, ascending.
+    __device__ double eval_rollout(u64 own, u64 opp, bool root_init)
+    {
+        for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri[a] = 1.0f;
+        int result = 0;
+        if (lane == 0) {
+            const uint32_t tag = ((uint32_t)c.ply << 1) | (root_init ? 1u : 0u);
+            const uint32_t ctr = (uint32_t)c.sims_done;
+            u64 o = own, p = opp;
+            int side = 0;  // 0: the leaf's side to move owns `o`
+            u64 m = legal_moves(o, p);
+            Philox4 r = {0, 0, 0, 0};
+            for (int nd = 0; nd < 128;) {  // nd = random draws so far (forced passes draw nothing)
+                if (m == 0) {
+                    const u64 m2 = legal_moves(p, o);
+                    if (m2 == 0) break;  // neither side can move: terminal
+                    const u64 t = o;
+                    o = p;
+                    p = t;
+                    side ^= 1;
+                    m = m2;
+                    continue;
+                }
+                if ((nd & 3) == 0) r = philox4x32_10(P.cfg.seed ^ kSaltRollout, (uint64_t)c.game_id, (uint32_t)ctr, tag | ((uint32_t)(nd >> 2) << 16));
+                const int w = nd & 3;
+                const uint32_t rnd = w == 0 ? r.x : (w == 1 ? r.y : (w == 2 ? r.z : r.w));
+                nd++;
+                const int sq = nth_set_bit(m, (int)__umulhi(rnd, (uint32_t)__popcll(m)));
+                const u64 f = flips(o, p, 1ULL << sq);
+                const Board b = apply_move(o, p, sq, f);
+                o = b.own;
+                p = b.opp;
+                side ^= 1;
+                m = legal_moves(o, p);
+            }
+            const int d = side == 0 ? __popcll(o) - __popcll(p) : __popcll(p) - __popcll(o);
+            result = (d > 0) - (d < 0);
+        }
+        result = gshfl(result, 0);
+        gsync();
+        return (double)result;
     }
 
     // Device twins of oracle/othello_oracle.c orc_stub_a/b/h: raw priors to S.pri, value returned.
@@ -883,7 +930,7 @@ struct Ctx {
             const bool root_init = (depth == 1);  // the leaf is the root: policy_improve_step :234-235
             const ulonglong2 lb = B[leaf];
             if (stub) {
-                const double value = eval_stub(lb.x, lb.y);
+                const double value = P.cfg.eval_kind == OTH_EVAL_ROLLOUT ? eval_rollout(lb.x, lb.y, root_init) : eval_stub(lb.x, lb.y);
                 const Node lf = load_node(N + leaf);
                 if (!expand(leaf, root_init, lf, lb, false)) break;
                 backup(depth, value);
@@ -1095,7 +1142,7 @@ int check_cfg(const oth_mcts_config* cfg)
     if (cfg->n_slots <= 0 || cfg->node_cap < 64 || cfg->path_cap < 2 || cfg->path_cap > 128) return OTH_E_ARG;
     if (cfg->num_simulations < 0 || cfg->max_inline_sims <= 0) return OTH_E_ARG;
     if (cfg->lanes != 8 && cfg->lanes != 16 && cfg->lanes != 32) return OTH_E_ARG;
-    if (cfg->eval_kind < OTH_EVAL_EXTERNAL || cfg->eval_kind > OTH_EVAL_STUB_H) return OTH_E_ARG;
+    if (cfg->eval_kind < OTH_EVAL_EXTERNAL || cfg->eval_kind > OTH_EVAL_ROLLOUT) return OTH_E_ARG;
     if (cfg->fused_softmax) return OTH_E_ARG;  // reserved
     if (cfg->self_play && (cfg->out_pos_cap <= 0 || cfg->out_game_cap <= 0)) return OTH_E_ARG;
     return OTH_OK;

@@ -124,6 +124,7 @@ int oth_host_random_read_probe(int64_t buffer_bytes, int32_t chunk_bytes, double
 #define OTH_EVAL_STUB_A 1   /* uniform priors, value 0 */
 #define OTH_EVAL_STUB_B 2   /* weighted-sum stub */
 #define OTH_EVAL_STUB_H 3   /* hash stub (oracle/othello_oracle.c orc_stub_h) */
+#define OTH_EVAL_ROLLOUT 4  /* policy=None: uniform priors + one random playout (MCTS_model.py:276-303, 332-335) */
 
 /* per-slot phases (oth_mcts_ctl.phase) */
 #define OTH_PH_RUN 0       /* searching, nothing pending */

@@ -62,6 +62,8 @@ def lib():
         L.orc_mcts_root_stats.argtypes = [vp, vp, vp, vp, vp, vp]
         L.orc_mcts_counters.argtypes = [vp, vp]
         L.orc_mcts_policy.argtypes = [vp, f64, f64, vp]
+        L.orc_mcts_set_rollout.argtypes = [vp, C.c_uint64, C.c_uint64]
+        L.orc_mcts_set_ply.argtypes = [vp, i32]
         L.orc_mcts_make_move.argtypes = [vp, i32]
         L.orc_mcts_make_move.restype = i32
         L.orc_self_play.argtypes = [f64, i32, f64, f64, i32, f64, vp, vp, vp, vp, vp, i32] + [vp] * 8
@@ -210,10 +212,16 @@ class OracleMCTS:
     """MCTS surface (MCTS_model.py:172-274), num_threads=1 semantics, with
     the reference's np.random draws replaced by injected values."""
 
-    def __init__(self, c_puct, num_simulations, evaluator, dirichlet_epsilon=0.0):
+    def __init__(self, c_puct, num_simulations, evaluator, dirichlet_epsilon=0.0, rollout_seed=0, game_id=0):
+        """evaluator=None selects the reference's policy=None mode (uniform priors + random playout)."""
         self.ev = evaluator
-        self.h = lib().orc_mcts_new(float(c_puct), int(num_simulations), float(dirichlet_epsilon),
-                                    evaluator.fn_ptr, evaluator.ctx)
+        if evaluator is None:
+            self.h = lib().orc_mcts_new(float(c_puct), int(num_simulations), float(dirichlet_epsilon), None, None)
+            lib().orc_mcts_set_rollout(self.h, int(rollout_seed), int(game_id))
+        else:
+            self.h = lib().orc_mcts_new(float(c_puct), int(num_simulations), float(dirichlet_epsilon),
+                                        evaluator.fn_ptr, evaluator.ctx)
+        self.ply = 0
 
     def __del__(self):
         try:
@@ -224,6 +232,7 @@ class OracleMCTS:
     def search(self, state, player, noise=None):
         if noise is not None:
             noise = np.ascontiguousarray(noise, dtype=np.float64)
+        lib().orc_mcts_set_ply(self.h, self.ply)
         rc = lib().orc_mcts_search(self.h, _p(_state(state)), int(player), _p(noise))
         if rc != 0:
             raise AssertionError("root does not match the given state/player")
@@ -240,6 +249,7 @@ class OracleMCTS:
     def make_move(self, action):
         if lib().orc_mcts_make_move(self.h, int(action)) != 0:
             raise KeyError(int(action))
+        self.ply += 1
 
     def root_stats(self):
         counts = np.zeros(65, np.int32)

@@ -119,3 +119,20 @@ def test_collect_self_play_games_small_net():
         assert g[-1][2] in (-1.0, 0.0, 1.0)
         for (s, pi, v) in g:
             assert abs(pi.sum() - 1) < 1e-5 and -1.0 <= v <= 1.0
+
+
+def test_mcts_class_rollout_mode_finds_forced_win():
+    """The reference's own MCTS tests use policy=None (test_MCTS.py:7-36, TicTacToe): a forced win must
+    get the visits.  Othello analogue: a position where one move wipes the opponent out."""
+    from alphazero_othello_b200.MCTS_model import MCTS
+    from alphazero_othello_b200.envs.othello import OthelloGameNew
+    env = OthelloGameNew(8)
+    s = np.zeros((8, 8), np.int8)
+    s[3, 2] = 1; s[3, 3] = -1; s[3, 4] = -1          # playing (3,5) captures every -1 disc: immediate win
+    s[0, 0] = 1; s[1, 0] = -1; s[5, 5] = 1; s[5, 6] = -1; s[2, 0] = 0
+    m = MCTS(env, {"c_puct": 1.4, "num_simulations": 300, "num_threads": 1}, None, seed=1)
+    probs = m.policy_improve_step(s, 1, temp=1.0)
+    assert m.use_rollout and abs(probs.sum() - 1) < 1e-5
+    legal = np.nonzero(env.get_valid_moves(s, 1))[0]
+    assert set(np.nonzero(probs)[0]) <= set(legal)
+    assert m.root.visit_count == 301

@@ -234,3 +234,40 @@ def test_node_overflow_fails_loudly():
     e = _selfplay_engine(args, 32, 2, False, 1, node_cap=64)
     with pytest.raises(_lib.OthelloB200Error, match="overflow"):
         _run_to_done(e, 400)
+
+
+@pytest.mark.parametrize("lanes", LANES)
+def test_rollout_evaluator_policy_none_vs_oracle(lanes):
+    """policy=None mode (MCTS_model.py:276-303, 332-335): uniform priors + a random playout per leaf,
+    playouts drawn from Philox on both sides -> bit-exact visit counts and root values."""
+    import torch
+    import oracle as O
+    from alphazero_othello_b200 import _lib
+    from alphazero_othello_b200.engine import MctsEngine
+    args = {"c_puct": 1.4, "num_simulations": 60, "dirichlet_epsilon": 0.0}
+    n = 6
+    e = MctsEngine(n, args, self_play=False, eval_kind=_lib.EVAL_ROLLOUT, lanes=lanes, seed=4242, max_inline_sims=1000, game_id_base=100)
+    g = O.OracleGame()
+    s0 = g.get_initial_state()
+    own, opp = _pack(s0, 1)
+    e.set_roots(torch.from_numpy(np.repeat(_i64(own), n)).cuda(), torch.from_numpy(np.repeat(_i64(opp), n)).cuda(),
+                torch.ones(n, dtype=torch.int8, device="cuda"))
+    refs = [O.OracleMCTS(1.4, 60, None, rollout_seed=4242, game_id=100 + i) for i in range(n)]
+    states, players = [s0.copy() for _ in range(n)], [1] * n
+    for mv in range(8):
+        _search(e)
+        st = {k: v.cpu().numpy() for k, v in e.root_stats().items()}
+        acts = []
+        for i in range(n):
+            refs[i].search(states[i], players[i])
+            r = refs[i].root_stats()
+            assert np.array_equal(st["counts"][i], r["counts"]), (mv, i)
+            assert st["root_value"][i] == r["root_value"] and st["root_n"][i] == r["root_n"]
+            a = int(np.argmax(r["counts"]))
+            acts.append(a)
+            refs[i].make_move(a)
+            states[i] = g.get_next_state(states[i], a, players[i])
+            players[i] = -players[i]
+        e.advance(torch.tensor(acts, dtype=torch.int32, device="cuda"))
+        e.raise_on_error()
+    assert len({tuple(st["counts"][i]) for i in range(n)}) > 1  # different game ids -> different playouts
