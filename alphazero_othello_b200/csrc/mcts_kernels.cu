@@ -866,6 +866,7 @@ struct Ctx {
         }
         load_counters();
         c = P.ctl[slot];
+        if (c.top < 1) return;  // slot never given a tree (zero-filled control block): nothing to do
         bind_arena();
         gsync();
         if (c.phase == OTH_PH_WAIT_EVAL) {
@@ -988,7 +989,7 @@ __global__ void __launch_bounds__(256) k_mcts_poll(const Params P)
         unsigned x = P.slot_counters[s * CNT_LOCAL + i];
         const oth_mcts_ctl* c = P.ctl + s;
         if (i == OTH_CNT_WAITING) x = c->phase == OTH_PH_WAIT_EVAL;
-        if (i == OTH_CNT_ACTIVE) x = (c->phase == OTH_PH_WAIT_EVAL || c->phase == OTH_PH_RUN);
+        if (i == OTH_CNT_ACTIVE) x = c->top >= 1 && (c->phase == OTH_PH_WAIT_EVAL || c->phase == OTH_PH_RUN);
         if (i == OTH_CNT_ERRORS) x = (c->phase == OTH_PH_ERROR || c->error != 0);
         if (i == OTH_CNT_MAX_TOP) x = (unsigned)c->top;
         v = is_max ? (x > v ? x : v) : v + x;
@@ -1026,13 +1027,15 @@ __global__ void __launch_bounds__(kBlock) k_mcts_reset(const Params P)
 }
 
 template <int LANES>
-__global__ void __launch_bounds__(kBlock) k_mcts_set_roots(const Params P, const u64* own, const u64* opp, const int8_t* players)
+__global__ void __launch_bounds__(kBlock) k_mcts_set_roots(const Params P, const u64* own, const u64* opp, const int8_t* players,
+                                                           const uint8_t* mask)
 {
     __shared__ Scratch scratch[kBlock / LANES];
     cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
     Ctx<LANES> ctx(tile, P, scratch[threadIdx.x / LANES]);
     const int groups = (gridDim.x * kBlock) / LANES;
     for (int s = (blockIdx.x * kBlock + threadIdx.x) / LANES; s < P.cfg.n_slots; s += groups) {
+        if (mask && !mask[s]) continue;
         ctx.slot = s;
         oth_mcts_ctl z = {};
         ctx.c = z;
@@ -1045,12 +1048,12 @@ __global__ void __launch_bounds__(kBlock) k_mcts_set_roots(const Params P, const
     }
 }
 
-__global__ void k_mcts_begin_search(const Params P)
+__global__ void k_mcts_begin_search(const Params P, const uint8_t* mask)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.cfg.n_slots) return;
+    if (s >= P.cfg.n_slots || (mask && !mask[s])) return;
     oth_mcts_ctl* c = P.ctl + s;
-    if (c->phase == OTH_PH_IDLE) {
+    if (c->phase == OTH_PH_IDLE && c->top >= 1) {
         c->sims_done = 0;
         c->phase = OTH_PH_RUN;
     }
@@ -1068,7 +1071,7 @@ __global__ void __launch_bounds__(kBlock) k_mcts_advance(const Params P, const i
         if (action < 0) continue;
         ctx.slot = s;
         ctx.c = P.ctl[s];
-        if (ctx.c.phase == OTH_PH_ERROR) continue;
+        if (ctx.c.phase == OTH_PH_ERROR || ctx.c.top < 1) continue;
         ctx.load_counters();
         ctx.bind_arena();
         tile.sync();
@@ -1242,26 +1245,35 @@ extern "C" int oth_mcts_reset(const oth_mcts_config* cfg, const oth_mcts_buffers
     return cuda_status(cudaGetLastError());
 }
 
-extern "C" int oth_mcts_set_roots(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const uint64_t* own, const uint64_t* opp,
-                                  const int8_t* players, void* stream)
+extern "C" int oth_mcts_set_roots_masked(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const uint64_t* own, const uint64_t* opp,
+                                         const int8_t* players, const uint8_t* mask, void* stream)
 {
     Params p;
     const int rc = make_params(cfg, b, &p);
     if (rc != OTH_OK) return rc;
     if (!own || !opp || !players) return OTH_E_ARG;
-    int e = cuda_status(cudaMemsetAsync(p.counters, 0, 16 * 8, (cudaStream_t)stream));
-    if (e != OTH_OK) return e;
-    LAUNCH_LANES(k_mcts_set_roots, mcts_grid(cfg), stream, p, (const u64*)own, (const u64*)opp, players);
+    LAUNCH_LANES(k_mcts_set_roots, mcts_grid(cfg), stream, p, (const u64*)own, (const u64*)opp, players, mask);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int oth_mcts_set_roots(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const uint64_t* own, const uint64_t* opp,
+                                  const int8_t* players, void* stream)
+{
+    return oth_mcts_set_roots_masked(cfg, b, own, opp, players, nullptr, stream);
+}
+
+extern "C" int oth_mcts_begin_search_masked(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const uint8_t* mask, void* stream)
+{
+    Params p;
+    const int rc = make_params(cfg, b, &p);
+    if (rc != OTH_OK) return rc;
+    k_mcts_begin_search<<<(cfg->n_slots + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, mask);
     return cuda_status(cudaGetLastError());
 }
 
 extern "C" int oth_mcts_begin_search(const oth_mcts_config* cfg, const oth_mcts_buffers* b, void* stream)
 {
-    Params p;
-    const int rc = make_params(cfg, b, &p);
-    if (rc != OTH_OK) return rc;
-    k_mcts_begin_search<<<(cfg->n_slots + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
-    return cuda_status(cudaGetLastError());
+    return oth_mcts_begin_search_masked(cfg, b, nullptr, stream);
 }
 
 extern "C" int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const float* priors, const float* values,

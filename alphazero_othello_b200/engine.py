@@ -124,12 +124,13 @@ class MctsEngine:
     def reset(self):
         self._call(self.L.oth_mcts_reset, self._stream())
 
-    def set_roots(self, own, opp, players):
-        """own/opp int64 [n_slots] device tensors, players int8 [n_slots]."""
-        self._call(self.L.oth_mcts_set_roots, own.data_ptr(), opp.data_ptr(), players.data_ptr(), self._stream())
+    def set_roots(self, own, opp, players, mask=None):
+        """own/opp int64 [n_slots] device tensors, players int8 [n_slots]; mask uint8 [n_slots] limits the slots."""
+        self._call(self.L.oth_mcts_set_roots_masked, own.data_ptr(), opp.data_ptr(), players.data_ptr(),
+                   None if mask is None else mask.data_ptr(), self._stream())
 
-    def begin_search(self):
-        self._call(self.L.oth_mcts_begin_search, self._stream())
+    def begin_search(self, mask=None):
+        self._call(self.L.oth_mcts_begin_search_masked, None if mask is None else mask.data_ptr(), self._stream())
 
     def step(self):
         """One launch of the fused expand/backup/select/self-play kernel on the engine's

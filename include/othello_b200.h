@@ -245,6 +245,13 @@ int oth_mcts_reset(const oth_mcts_config* cfg, const oth_mcts_buffers* b, void* 
 int oth_mcts_set_roots(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const uint64_t* own, const uint64_t* opp,
                        const int8_t* players, void* stream);
 
+/* As oth_mcts_set_roots / oth_mcts_begin_search, restricted to slots with mask[slot] != 0
+ * (device uint8 [n_slots]; NULL = all).  The batched arena (eval.py:134-178) uses them: in every
+ * ply only the trees of the side to move search. */
+int oth_mcts_set_roots_masked(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const uint64_t* own, const uint64_t* opp,
+                              const int8_t* players, const uint8_t* mask, void* stream);
+int oth_mcts_begin_search_masked(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const uint8_t* mask, void* stream);
+
 /* Manual mode: begin a search of num_simulations on every idle slot
  * (MCTS.policy_improve_step, MCTS_model.py:234-242). */
 int oth_mcts_begin_search(const oth_mcts_config* cfg, const oth_mcts_buffers* b, void* stream);
