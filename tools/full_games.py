@@ -1,0 +1,44 @@
+"""Complete self-play batches (every game played to the end) for C3 / C4: whole-game throughput,
+arena high-water mark, depth -- the numbers DESIGN.md quotes beside the short default bench."""
+import json
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from alphazero_othello_b200 import _lib
+from alphazero_othello_b200.Models import fold_for_inference
+from alphazero_othello_b200.engine import BatchedPolicy, MctsEngine, SelfPlayRunner
+from bench import TRAIN_ARGS, WORKLOADS, make_net
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "c3"
+desc, kind, G, sims = WORKLOADS[wl]
+args = dict(TRAIN_ARGS, num_simulations=sims)
+dev = torch.device("cuda:0")
+net = fold_for_inference(make_net(kind).to(dev), torch.bfloat16)
+eng = MctsEngine(G, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=1, device=dev, seed=1)
+run = SelfPlayRunner(eng, BatchedPolicy(net, dev, torch.float32))
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+run.warm_start()
+it, max_top = 0, 0
+while True:
+    run.run_iterations(256)
+    it += 256
+    c = eng.counters()
+    max_top = max(max_top, c["max_top"])
+    if c["errors"]:
+        eng.raise_on_error()
+    if c["active"] == 0:
+        break
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+out = eng.drain()
+c = eng.counters()
+print(json.dumps({"workload": f"{wl}: {desc}", "complete_games": int(out["games"].shape[0]), "positions": int(out["values"].numel()),
+                  "seconds": dt, "iterations": it, "sims": c["sims"], "sims_per_s": c["sims"] / dt, "positions_per_s": out["values"].numel() / dt,
+                  "terminal_sim_fraction": c["terminal_sims"] / c["sims"], "mean_plies": out["values"].numel() / out["games"].shape[0],
+                  "arena_high_water": max_top, "node_cap": eng.cfg.node_cap, "max_depth": c["max_depth"],
+                  "nodes_created": c["nodes"], "nodes_copied_by_reroot": c["copied"],
+                  "mean_levels_per_sim": c["levels"] / c["sims"], "mean_children_per_level": c["children"] / max(c["levels"], 1)}))
