@@ -23,7 +23,7 @@ ERR_NAMES = {1: "node arena overflow", 2: "path overflow", 4: "output ring overf
 
 (BUF_NODES, BUF_BOARDS, BUF_CTL, BUF_PATH, BUF_ROOT_PRIOR64, BUF_NOISE, BUF_U_MOVE, BUF_U_TIE, BUF_TRAJ_BOARD,
  BUF_TRAJ_PI, BUF_TRAJ_ROOTV, BUF_TRAJ_META, BUF_OUT_BOARD, BUF_OUT_PI, BUF_OUT_VALUE, BUF_OUT_META, BUF_OUT_GAMES,
- BUF_COUNTERS, BUF_SLOT_COUNTERS, BUF_COUNT) = range(20)
+ BUF_COUNTERS, BUF_SLOT_COUNTERS, BUF_HOT, BUF_COUNT) = range(21)
 
 (CNT_SIMS, CNT_EVALS, CNT_TERMINAL, CNT_GAMES, CNT_POSITIONS, CNT_OUT_GAMES, CNT_MOVES, CNT_ERRORS, CNT_MAX_TOP,
  CNT_MAX_DEPTH, CNT_NODES, CNT_COPIED, CNT_WAITING, CNT_ACTIVE, CNT_LEVELS, CNT_CHILDREN) = range(16)

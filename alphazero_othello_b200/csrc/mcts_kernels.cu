@@ -56,12 +56,14 @@ __device__ __forceinline__ uint32_t make_meta(int nchild, int action, uint32_t f
     return (uint32_t)nchild | ((uint32_t)action << 8) | (flags << 16) | (((uint32_t)tv & 0xffu) << 24);
 }
 
-// Two 128-bit accesses per record.  Plain (coherent) loads: records are
-// rewritten by this group within the same launch.
+// Two 128-bit accesses per record, always served by L2 (ld.global.cg): visit counts and value
+// sums are updated by fire-and-forget L2 reductions (backup), so no record line may sit in L1.
+__device__ __forceinline__ uint4 ldcg4(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+
 __device__ __forceinline__ Node load_node(const Node* p)
 {
-    const uint4 a = *reinterpret_cast<const uint4*>(p);
-    const uint4 b = *(reinterpret_cast<const uint4*>(p) + 1);
+    const uint4 a = ldcg4(p);
+    const uint4 b = ldcg4(reinterpret_cast<const uint4*>(p) + 1);
     Node n;
     n.W = __hiloint2double((int)a.y, (int)a.x);
     n.prior = __uint_as_float(a.z);
@@ -108,6 +110,7 @@ struct Params {
     long long* out_games;
     unsigned long long* counters;
     unsigned* slot_counters;  // [slot][16] cumulative event counters, summed by k_mcts_poll
+    uint4* hot;               // [slot] 256-byte SlotHot records
     const float* priors;
     const float* values;
     float* nn_input;
@@ -117,12 +120,30 @@ struct Params {
 // per-group scratch in shared memory
 enum { CNT_LOCAL = 16 };
 
+// Everything a slot needs at the start of a launch, in one 256-byte record fetched together
+// with the control block: the pending leaf (board, legal set, meta word) so expansion can start
+// without a second round trip, a mirror of the root's header so the descent starts without
+// reading the root record, and the first 52 entries of the search path.
+constexpr int kHotPath = 52;
+struct __align__(16) SlotHot {
+    u64 leaf_own, leaf_opp, leaf_moves;
+    uint32_t leaf_meta;
+    int32_t root_N;  // == visit_count of the root record
+    int32_t root_fc;  // == first_child of the root record (-1: leaf)
+    uint32_t root_meta;
+    int32_t pad[2];
+    int32_t path[kHotPath];
+};
+static_assert(sizeof(SlotHot) == 256 && offsetof(SlotHot, path) == 48, "SlotHot layout");
+
 struct __align__(16) Scratch {
     double pri64[OTH_NUM_ACTIONS + 1];
     float pri[OTH_NUM_ACTIONS + 3];
-    int path[128];
+    SlotHot hot;               // hot.path continues into path_tail: 52 + 76 = 128 entries
+    int path_tail[128 - kHotPath];
     unsigned cnt[CNT_LOCAL];  // the slot's cumulative event counters while it is being worked on
 };
+static_assert(offsetof(Scratch, path_tail) == offsetof(Scratch, hot) + 256, "path must be contiguous");
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -182,6 +203,36 @@ struct Ctx {
     __device__ __forceinline__ void count_max(int which, unsigned v)
     {
         if (lane == 0 && v > S.cnt[which]) S.cnt[which] = v;
+    }
+
+    // first 80 bytes (header + 8 path entries) are requested with the control block; the rest of
+    // the path only if it is that deep
+    __device__ __forceinline__ void load_hot_head()
+    {
+        const uint4* g = P.hot + (size_t)slot * 16;
+        uint4* d = reinterpret_cast<uint4*>(&S.hot);
+        for (int i = lane; i < 5; i += LANES) d[i] = g[i];
+    }
+    __device__ __forceinline__ void load_path_rest(int path_len)
+    {
+        if (path_len > 8) {
+            const uint4* g = P.hot + (size_t)slot * 16;
+            uint4* d = reinterpret_cast<uint4*>(&S.hot);
+            const int n16 = 3 + (min(path_len, kHotPath) + 3) / 4;
+            for (int i = 5 + lane; i < n16; i += LANES) d[i] = g[i];
+            const int* gp = P.path + (size_t)slot * P.cfg.path_cap;
+            for (int k = kHotPath + lane; k < path_len; k += LANES) S.hot.path[k] = gp[k];
+        }
+    }
+    __device__ __forceinline__ void store_hot(int path_len)
+    {
+        gsync();
+        uint4* g = P.hot + (size_t)slot * 16;
+        const uint4* d = reinterpret_cast<const uint4*>(&S.hot);
+        const int n16 = 3 + (min(path_len, kHotPath) + 3) / 4;
+        for (int i = lane; i < n16; i += LANES) g[i] = d[i];
+        int* gp = P.path + (size_t)slot * P.cfg.path_cap;
+        for (int k = kHotPath + lane; k < path_len; k += LANES) gp[k] = S.hot.path[k];
     }
 
     __device__ __forceinline__ void bind_arena()
@@ -446,24 +497,29 @@ struct Ctx {
         }
         c.top = fc + nchild;
         if (f64) c.flags |= 2;
-        if (root_init) {  // prefetch hints for the next launches (never read for semantics)
-            c.reserved = (long long)(unsigned)fc | ((long long)nchild << 32);
+        if (leaf == c.root && lane == 0) {  // keep the root mirror exact
+            S.hot.root_fc = fc;
+            S.hot.root_meta = (lf.meta & ~0xffu) | (uint32_t)nchild;
         }
         count(OTH_CNT_NODES, nchild);
         gsync();
         return true;
     }
 
-    // Node.backpropagate (MCTS_model.py:160-169) along S.path[0..depth).
+    // Node.backpropagate (MCTS_model.py:160-169) along S.hot.path[0..depth).
     __device__ __forceinline__ void backup(int depth, double value)
     {
         gsync();
+        // one float64 add and one integer add per path node, performed by the L2 (RED, no return
+        // value): nothing is loaded, the group does not wait.  A single IEEE add per node per
+        // simulation, in simulation order -> same sums as the reference's sequential loop.
         for (int d = lane; d < depth; d += LANES) {
-            Node* p = N + S.path[d];
+            Node* p = N + S.hot.path[d];
             const double sv = ((depth - 1 - d) & 1) ? -value : value;
-            p->N += 1;
-            p->W = __dadd_rn(p->W, sv);
+            atomicAdd(&p->N, 1);
+            atomicAdd(&p->W, sv);
         }
+        if (lane == 0) S.hot.root_N += 1;  // every path starts at the root
         gsync();
     }
 
@@ -474,7 +530,10 @@ struct Ctx {
     __device__ int descend(int& leaf, int& depth, Node& nd)
     {
         int cur = c.root;
-        nd = load_node(N + cur);
+        nd.N = S.hot.root_N;  // root header from the mirror: no record load on the critical path
+        nd.first_child = S.hot.root_fc;
+        nd.meta = S.hot.root_meta;
+        nd.moves = 0;
         depth = 0;
         const double cp64 = P.cfg.c_puct;
         const float cp32 = P.c_puct_f32;
@@ -483,7 +542,7 @@ struct Ctx {
                 fail(OTH_ERR_PATH_OVERFLOW);
                 return -1;
             }
-            if (lane == 0) S.path[depth] = cur;
+            if (lane == 0) S.hot.path[depth] = cur;
             depth++;
             leaf = cur;
             if (meta_flags(nd.meta) & kFlagTerminal) return 1;
@@ -495,6 +554,7 @@ struct Ctx {
             int bi = 0x7fffffff;
             int k_N = 0, k_fc = -1;
             uint32_t k_meta = 0;
+            u64 k_moves = 0;
             if (!f64) {
                 float bs = -INFINITY;
                 for (int i = lane; i < nchild; i += LANES) {
@@ -510,6 +570,7 @@ struct Ctx {
                         k_N = ch.N;
                         k_fc = ch.first_child;
                         k_meta = ch.meta;
+                        k_moves = ch.moves;
                     }
                 }
                 const float m = redux_max_f32(bs, gmask);
@@ -529,6 +590,7 @@ struct Ctx {
                         k_N = ch.N;
                         k_fc = ch.first_child;
                         k_meta = ch.meta;
+                        k_moves = ch.moves;
                     }
                 }
 #pragma unroll
@@ -545,6 +607,7 @@ struct Ctx {
             nd.N = gshfl(k_N, src);
             nd.first_child = gshfl(k_fc, src);
             nd.meta = gshfl(k_meta, src);
+            if (nd.first_child < 0) nd.moves = gshfl(k_moves, src);  // a leaf: its legal set is what expansion needs
             cur = fc + bi;
             // the chosen child's board is needed only if it turns out to be the leaf: start fetching it now
             prefetch_l2(B + cur);
@@ -579,6 +642,11 @@ struct Ctx {
         c.flags = 0;
         c.reserved = -1;
         c.phase = OTH_PH_RUN;
+        if (lane == 0) {
+            S.hot.root_N = 0;
+            S.hot.root_fc = -1;
+            S.hot.root_meta = make_meta(0, 0xff, 0u, 0);
+        }
         gsync();
     }
 
@@ -605,7 +673,7 @@ struct Ctx {
             const int chunk = min(LANES, top - i);
             int ofc = -1, nch = 0;
             if (lane < chunk) {
-                const uint4 b = *(reinterpret_cast<const uint4*>(Nd + i + lane) + 1);
+                const uint4 b = ldcg4(reinterpret_cast<const uint4*>(Nd + i + lane) + 1);
                 ofc = (int)b.x;
                 nch = ofc >= 0 ? (int)(b.y & 0xffu) : 0;
             }
@@ -626,7 +694,7 @@ struct Ctx {
                 for (int j = lane; j < n_; j += LANES) {
                     const uint4* s = reinterpret_cast<const uint4*>(Ns + o_ + j);
                     uint4* d = reinterpret_cast<uint4*>(Nd + d_ + j);
-                    const uint4 x0 = s[0], x1 = s[1];
+                    const uint4 x0 = ldcg4(s), x1 = ldcg4(s + 1);
                     const ulonglong2 bb = Bs[o_ + j];
                     d[0] = x0;
                     d[1] = x1;
@@ -641,10 +709,13 @@ struct Ctx {
         c.root = 0;
         c.top = top;
         c.flags &= ~2;
-        {  // prefetch hint: where the new root's children now live
-            const uint4 b = *(reinterpret_cast<const uint4*>(Nd) + 1);
-            c.reserved = (int)b.x >= 0 ? ((long long)b.x | ((long long)(b.y & 0xffu) << 32)) : -1;
+        if (lane == 0) {  // root mirror of the new root
+            const Node r = load_node(Nd);
+            S.hot.root_N = r.N;
+            S.hot.root_fc = r.first_child;
+            S.hot.root_meta = r.meta;
         }
+        gsync();
     }
 
     // ------------------------------------------------ policy target etc --
@@ -810,7 +881,7 @@ struct Ctx {
         int ci = -1;
         uint32_t cmeta = 0;
         for (int i = lane; i < nchild; i += LANES) {
-            const uint4 b = *(reinterpret_cast<const uint4*>(N + fc + i) + 1);
+            const uint4 b = ldcg4(reinterpret_cast<const uint4*>(N + fc + i) + 1);
             if (meta_action(b.y) == action) {
                 ci = i;
                 cmeta = b.y;
@@ -865,25 +936,26 @@ struct Ctx {
             nn_value = P.values[slot];
         }
         load_counters();
+        load_hot_head();
         c = P.ctl[slot];
         if (c.top < 1) return;  // slot never given a tree (zero-filled control block): nothing to do
         bind_arena();
         gsync();
-        if (c.phase == OTH_PH_WAIT_EVAL) {
-            // (2) second round trip: leaf record + board, the path, and L2 prefetches of what
-            //     backup and the next descent will touch (path nodes, root, root's children)
-            const Node lf = load_node(N + c.pending);
-            const ulonglong2 lb = B[c.pending];
-            const int* gp = P.path + (size_t)slot * P.cfg.path_cap;
-            for (int d = lane; d < c.path_len; d += LANES) {
-                const int idx = gp[d];
-                S.path[d] = idx;
-                prefetch_l2(N + idx);
-            }
-            if (c.reserved >= 0) {
-                const int rfc = (int)(c.reserved & 0xffffffffLL), rn = (int)(c.reserved >> 32);
+        if (c.phase == OTH_PH_WAIT_EVAL || c.phase == OTH_PH_RUN) {
+            // the next descent starts at the root's children: get them into L2 now
+            const int rfc = S.hot.root_fc, rn = meta_nchild(S.hot.root_meta);
+            if (rfc >= 0)
                 for (int i = lane; i < rn; i += LANES) prefetch_l2(N + rfc + i);
-            }
+        }
+        if (c.phase == OTH_PH_WAIT_EVAL) {
+            // (2) no second round trip: the pending leaf's board / legal set / meta word and the
+            //     path came with the hot record (only paths deeper than 8 need more of it)
+            load_path_rest(c.path_len);
+            Node lf;
+            lf.moves = S.hot.leaf_moves;
+            lf.meta = S.hot.leaf_meta;
+            lf.first_child = -1;
+            const ulonglong2 lb = make_ulonglong2(S.hot.leaf_own, S.hot.leaf_opp);
 #pragma unroll
             for (int k = 0; k < NPL; k++) {  // priors *= valid_mask (:346) fused into the staging store
                 const int a = lane + k * LANES;
@@ -930,10 +1002,14 @@ struct Ctx {
             }
             const bool root_init = (depth == 1);  // the leaf is the root: policy_improve_step :234-235
             const ulonglong2 lb = B[leaf];
+            if (root_init) {  // the mirror has no legal set: read the root record (once per game at most)
+                const Node rr = load_node(N + leaf);
+                nd.moves = rr.moves;
+                nd.meta = rr.meta;
+            }
             if (stub) {
                 const double value = P.cfg.eval_kind == OTH_EVAL_ROLLOUT ? eval_rollout(lb.x, lb.y, root_init) : eval_stub(lb.x, lb.y);
-                const Node lf = load_node(N + leaf);
-                if (!expand(leaf, root_init, lf, lb, false)) break;
+                if (!expand(leaf, root_init, nd, lb, false)) break;
                 backup(depth, value);
                 if (!root_init) {
                     c.sims_done++;
@@ -949,11 +1025,15 @@ struct Ctx {
             c.flags = (c.flags & ~1) | (root_init ? 1 : 0);
             c.phase = OTH_PH_WAIT_EVAL;
             write_nn_input(lb.x, lb.y);
-            gsync();
-            int* gp = P.path + (size_t)slot * P.cfg.path_cap;
-            for (int d = lane; d < depth; d += LANES) gp[d] = S.path[d];
+            if (lane == 0) {  // what the expansion in the next launch needs, carried in the hot record
+                S.hot.leaf_own = lb.x;
+                S.hot.leaf_opp = lb.y;
+                S.hot.leaf_moves = nd.moves;
+                S.hot.leaf_meta = nd.meta;
+            }
         }
         if (lane == 0) P.ctl[slot] = c;
+        store_hot(c.phase == OTH_PH_WAIT_EVAL ? c.path_len : 0);
         store_counters();
         gsync();
     }
@@ -1023,6 +1103,8 @@ __global__ void __launch_bounds__(kBlock) k_mcts_reset(const Params P)
         if (P.cfg.games_per_slot == 0) ctx.c.phase = OTH_PH_DONE;
         for (int i = ctx.lane; i < CNT_LOCAL; i += LANES) P.slot_counters[(size_t)s * CNT_LOCAL + i] = 0;
         if (ctx.lane == 0) P.ctl[s] = ctx.c;
+        ctx.store_hot(0);
+        tile.sync();
     }
 }
 
@@ -1045,6 +1127,8 @@ __global__ void __launch_bounds__(kBlock) k_mcts_set_roots(const Params P, const
         ctx.c.phase = OTH_PH_IDLE;
         for (int i = ctx.lane; i < CNT_LOCAL; i += LANES) P.slot_counters[(size_t)s * CNT_LOCAL + i] = 0;
         if (ctx.lane == 0) P.ctl[s] = ctx.c;
+        ctx.store_hot(0);
+        tile.sync();
     }
 }
 
@@ -1073,13 +1157,14 @@ __global__ void __launch_bounds__(kBlock) k_mcts_advance(const Params P, const i
         ctx.c = P.ctl[s];
         if (ctx.c.phase == OTH_PH_ERROR || ctx.c.top < 1) continue;
         ctx.load_counters();
+        ctx.load_hot_head();
         ctx.bind_arena();
         tile.sync();
         const Node root = load_node(ctx.N + ctx.c.root);
         const int fc = root.first_child, nchild = root.first_child < 0 ? 0 : meta_nchild(root.meta);
         int ci = -1;
         for (int i = ctx.lane; i < nchild; i += LANES) {
-            const uint4 b = *(reinterpret_cast<const uint4*>(ctx.N + fc + i) + 1);
+            const uint4 b = ldcg4(reinterpret_cast<const uint4*>(ctx.N + fc + i) + 1);
             if (meta_action(b.y) == action) ci = i;
         }
         const unsigned hit = tile.ballot(ci >= 0);
@@ -1094,6 +1179,7 @@ __global__ void __launch_bounds__(kBlock) k_mcts_advance(const Params P, const i
             ctx.c.phase = OTH_PH_IDLE;
         }
         if (ctx.lane == 0) P.ctl[s] = ctx.c;
+        ctx.store_hot(0);
         ctx.store_counters();
         tile.sync();
     }
@@ -1181,6 +1267,7 @@ int make_params(const oth_mcts_config* cfg, const oth_mcts_buffers* b, Params* p
     p->out_games = (long long*)b->buf[OTH_BUF_OUT_GAMES];
     p->counters = (unsigned long long*)b->buf[OTH_BUF_COUNTERS];
     p->slot_counters = (unsigned*)b->buf[OTH_BUF_SLOT_COUNTERS];
+    p->hot = (uint4*)b->buf[OTH_BUF_HOT];
     p->priors = nullptr;
     p->values = nullptr;
     p->nn_input = nullptr;
@@ -1231,6 +1318,7 @@ extern "C" int oth_mcts_buffer_bytes(const oth_mcts_config* cfg, int64_t* out)
     out[OTH_BUF_OUT_GAMES] = sp ? cfg->out_game_cap * 32 : 0;
     out[OTH_BUF_COUNTERS] = 16 * 8;
     out[OTH_BUF_SLOT_COUNTERS] = G * CNT_LOCAL * 4;
+    out[OTH_BUF_HOT] = G * 256;
     return OTH_OK;
 }
 
