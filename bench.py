@@ -371,11 +371,17 @@ def aux_env(dev):
     _lib.check(_lib.lib().oth_host_rollout(9, 0, n, sc.ctypes.data, pl.ctypes.data, None, 0, None, None, C.byref(tot), C.byref(k2)))
     t1 = time.perf_counter()
     steps_s = best[1] / (best[0] * 1e-3)
+    ncu = {}
+    prof = os.path.join(ROOT, "profiles", "r01_rollout_c1.json")
+    if os.path.exists(prof):  # committed `ncu --set full` capture of the same kernel and size
+        pj = json.load(open(prof))
+        ncu = {"alu_pipe_pct_of_peak_ncu": pj["alu_pipe_pct_of_peak"], "thread_instructions_per_ply_ncu": pj["thread_instructions_per_ply"]}
     return {"workload": "c1: Othello 8x8 random-policy rollouts, 2^22 games", "env_steps_per_s": steps_s, "kernel_ms": best[0],
             "plies": best[1], "e2e_env_steps_per_s": tot.value / (t1 - t0), "e2e_d2h_bytes": n * 8,
             "int32_roofline": {"bound": "int32-alu", "instr_per_ply": 600, "achieved_ginstr_s": steps_s * 600 / 1e9,
                                "peak_ginstr_s": ips.value / 1e9, "frac": steps_s * 600 / ips.value,
-                               "peak_source": "measured live: LOP3+IADD3 probe kernel (oth_host_int32_peak)"}}
+                               "peak_source": "measured live: LOP3+IADD3 probe kernel (oth_host_int32_peak; it issues to the ALU and FMA pipes, "
+                                              "k_rollout's shift/logic mix can only use the ALU pipe)", **ncu}}
 
 
 def aux_search_only(dev, G, sims, lanes):
