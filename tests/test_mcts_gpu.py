@@ -6,7 +6,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-LANES = [32, 8]
+LANES = [32, 16, 8]
 
 
 def _pack(state, player):
