@@ -17,13 +17,13 @@ OTH_OK, OTH_E_CUDA, OTH_E_ARG, OTH_E_ILLEGAL, OTH_E_NO_DEVICE = 0, -1, -2, -3, -
 F_ILLEGAL, F_TERMINAL, F_WIN, F_LOSS, F_MUST_PASS = 1, 2, 4, 8, 16
 
 EVAL_EXTERNAL, EVAL_STUB_A, EVAL_STUB_B, EVAL_STUB_H, EVAL_ROLLOUT = 0, 1, 2, 3, 4
-PH_RUN, PH_WAIT_EVAL, PH_IDLE, PH_DONE, PH_ERROR = 0, 1, 2, 3, 4
+PH_RUN, PH_WAIT_EVAL, PH_IDLE, PH_DONE, PH_ERROR, PH_MOVE = 0, 1, 2, 3, 4, 5
 ERR_NAMES = {1: "node arena overflow", 2: "path overflow", 4: "output ring overflow", 8: "ply overflow",
              16: "action has no child (KeyError)"}
 
 (BUF_NODES, BUF_BOARDS, BUF_CTL, BUF_PATH, BUF_ROOT_PRIOR64, BUF_NOISE, BUF_U_MOVE, BUF_U_TIE, BUF_TRAJ_BOARD,
  BUF_TRAJ_PI, BUF_TRAJ_ROOTV, BUF_TRAJ_META, BUF_OUT_BOARD, BUF_OUT_PI, BUF_OUT_VALUE, BUF_OUT_META, BUF_OUT_GAMES,
- BUF_COUNTERS, BUF_SLOT_COUNTERS, BUF_HOT, BUF_COUNT) = range(21)
+ BUF_COUNTERS, BUF_SLOT_COUNTERS, BUF_HOT, BUF_MOVE_FLAGS, BUF_COUNT) = range(22)
 
 (CNT_SIMS, CNT_EVALS, CNT_TERMINAL, CNT_GAMES, CNT_POSITIONS, CNT_OUT_GAMES, CNT_MOVES, CNT_ERRORS, CNT_MAX_TOP,
  CNT_MAX_DEPTH, CNT_NODES, CNT_COPIED, CNT_WAITING, CNT_ACTIVE, CNT_LEVELS, CNT_CHILDREN) = range(16)

@@ -111,6 +111,7 @@ struct Params {
     unsigned long long* counters;
     unsigned* slot_counters;  // [slot][16] cumulative event counters, summed by k_mcts_poll
     uint4* hot;               // [slot] 256-byte SlotHot records
+    uint8_t* move_flags;      // [slot] set by the step kernel when a slot's move is due (k_mcts_move clears it)
     const float* priors;
     const float* values;
     float* nn_input;
@@ -443,8 +444,7 @@ struct Ctx {
         const bool f64 = root_init && P.cfg.dirichlet_epsilon > 0.0;
         float sum32 = 0.0f;
         if (f64) {
-            make_noise();
-            const double* nz = P.noise + (size_t)slot * OTH_NUM_ACTIONS;
+            const double* nz = P.noise + (size_t)slot * OTH_NUM_ACTIONS;  // drawn when the tree was created (init_tree) or injected
             const double eps = P.cfg.dirichlet_epsilon;
             const float om = (float)(1.0 - eps);  // (1-eps)*priors stays float32 (NEP 50)
             for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) {
@@ -648,6 +648,7 @@ struct Ctx {
             S.hot.root_meta = make_meta(0, 0xff, 0u, 0);
         }
         gsync();
+        if (P.cfg.dirichlet_epsilon > 0.0) make_noise();  // this tree's root noise (kept out of the hot kernel)
     }
 
     // ---------------------------------------------------------- re-root --
@@ -668,37 +669,78 @@ struct Ctx {
             Bd[0] = Bs[new_root];
         }
         gsync();
+        // Breadth-first: the destination arena is the queue.  Each pass takes up to PER*LANES queued
+        // nodes (all their headers are requested together), lays their child blocks out back to
+        // back, then copies all those children as one flat list with PER copies in flight per lane --
+        // two dependent round trips per pass instead of one per expanded node.
+        constexpr int PER = LANES == 32 ? 2 : 4, CH = LANES * PER;
+        static_assert((2 * CH + 1) * sizeof(int) <= sizeof(S.pri64), "re-root scratch must fit in pri64");
+        int* s_ofc = reinterpret_cast<int*>(S.pri64);  // [CH] old first_child per queued node (scratch is free here)
+        int* s_exc = s_ofc + CH;                        // [CH+1] exclusive prefix of child counts
         int top = 1, i = 0;
         while (i < top) {
-            const int chunk = min(LANES, top - i);
-            int ofc = -1, nch = 0;
-            if (lane < chunk) {
-                const uint4 b = ldcg4(reinterpret_cast<const uint4*>(Nd + i + lane) + 1);
-                ofc = (int)b.x;
-                nch = ofc >= 0 ? (int)(b.y & 0xffu) : 0;
-            }
-            int incl = nch;
+            const int chunk = min(CH, top - i);
+            int ofc[PER], nch[PER];
 #pragma unroll
-            for (int o = 1; o < LANES; o <<= 1) {
-                const int t = gshfl_up(incl, o);
-                if (lane >= o) incl += t;
+            for (int j = 0; j < PER; j++) {
+                const int k = j * LANES + lane;
+                ofc[j] = -1;
+                nch[j] = 0;
+                if (k < chunk) {
+                    const uint4 b = ldcg4(reinterpret_cast<const uint4*>(Nd + i + k) + 1);
+                    ofc[j] = (int)b.x;
+                    nch[j] = ofc[j] >= 0 ? (int)(b.y & 0xffu) : 0;
+                }
             }
-            const int excl = incl - nch;
-            const int total = gshfl(incl, LANES - 1);
-            if (lane < chunk && nch > 0) Nd[i + lane].first_child = top + excl;
-            unsigned pm = gballot(nch > 0);
-            while (pm) {
-                const int l = __ffs(pm) - 1;
-                pm &= pm - 1;
-                const int o_ = gshfl(ofc, l), n_ = gshfl(nch, l), d_ = top + gshfl(excl, l);
-                for (int j = lane; j < n_; j += LANES) {
-                    const uint4* s = reinterpret_cast<const uint4*>(Ns + o_ + j);
-                    uint4* d = reinterpret_cast<uint4*>(Nd + d_ + j);
-                    const uint4 x0 = ldcg4(s), x1 = ldcg4(s + 1);
-                    const ulonglong2 bb = Bs[o_ + j];
-                    d[0] = x0;
-                    d[1] = x1;
-                    Bd[d_ + j] = bb;
+            int base = 0;
+#pragma unroll
+            for (int j = 0; j < PER; j++) {
+                int incl = nch[j];
+#pragma unroll
+                for (int o = 1; o < LANES; o <<= 1) {
+                    const int t = gshfl_up(incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int excl = base + incl - nch[j];
+                const int k = j * LANES + lane;
+                s_ofc[k] = ofc[j];
+                s_exc[k] = excl;
+                if (k < chunk && nch[j] > 0) Nd[i + k].first_child = top + excl;
+                base += gshfl(incl, LANES - 1);
+            }
+            const int total = base;
+            gsync();
+            for (int t0 = 0; t0 < total; t0 += CH) {
+                uint4 x0[PER], x1[PER];
+                ulonglong2 bb[PER];
+                int dst[PER];
+#pragma unroll
+                for (int j = 0; j < PER; j++) {
+                    const int t = t0 + j * LANES + lane;
+                    dst[j] = -1;
+                    if (t < total) {
+                        int lo = 0, hi = chunk;  // last queued node whose child range starts at or before t
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if (s_exc[mid] <= t) lo = mid;
+                            else hi = mid;
+                        }
+                        const int src = s_ofc[lo] + (t - s_exc[lo]);
+                        const uint4* sp = reinterpret_cast<const uint4*>(Ns + src);
+                        x0[j] = ldcg4(sp);
+                        x1[j] = ldcg4(sp + 1);
+                        bb[j] = Bs[src];
+                        dst[j] = top + t;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < PER; j++) {
+                    if (dst[j] >= 0) {
+                        uint4* d = reinterpret_cast<uint4*>(Nd + dst[j]);
+                        d[0] = x0[j];
+                        d[1] = x1[j];
+                        Bd[dst[j]] = bb[j];
+                    }
                 }
             }
             top += total;
@@ -918,15 +960,20 @@ struct Ctx {
     }
 
     // ------------------------------------------------------ slot driver --
+    // MOVE: this instantiation may finish moves (policy target, sampling, re-rooting, game
+    //       hand-off).  The hot kernel (MOVE = false) only flags such slots; k_mcts_move picks
+    //       them up in the same oth_mcts_step call with a full warp per slot.
+    // STUB: device evaluators compiled in (search-only / test builds of the kernel).
+    template <bool MOVE, bool STUB>
     __device__ void run_slot()
     {
         // (1) everything that depends only on the slot index is requested at once:
         //     control block, network outputs for the pending leaf
         constexpr int NPL = (OTH_NUM_ACTIONS + LANES - 1) / LANES;
-        const bool stub = P.cfg.eval_kind != OTH_EVAL_EXTERNAL;
+        constexpr bool stub = STUB;
         float pv[NPL];
         float nn_value = 0.0f;
-        if (!stub) {
+        if (!stub && !(MOVE && !STUB)) {
             const float* pr = P.priors + (size_t)slot * OTH_NUM_ACTIONS;
 #pragma unroll
             for (int k = 0; k < NPL; k++) {
@@ -947,7 +994,13 @@ struct Ctx {
             if (rfc >= 0)
                 for (int i = lane; i < rn; i += LANES) prefetch_l2(N + rfc + i);
         }
-        if (c.phase == OTH_PH_WAIT_EVAL) {
+        if constexpr (MOVE) {
+            if (c.phase == OTH_PH_MOVE) {
+                c.phase = OTH_PH_RUN;
+                finish_move();
+            }
+        }
+        if (!(MOVE && !STUB) && c.phase == OTH_PH_WAIT_EVAL) {
             // (2) no second round trip: the pending leaf's board / legal set / meta word and the
             //     path came with the hot record (only paths deeper than 8 need more of it)
             load_path_rest(c.path_len);
@@ -984,9 +1037,15 @@ struct Ctx {
                     c.phase = OTH_PH_IDLE;
                     break;
                 }
-                finish_move();
-                budget--;
-                continue;
+                if constexpr (MOVE) {
+                    finish_move();
+                    budget--;
+                    continue;
+                } else {
+                    c.phase = OTH_PH_MOVE;  // the move kernel of this same step takes over
+                    if (lane == 0) P.move_flags[slot] = 1;
+                    break;
+                }
             }
             int leaf, depth;
             Node nd;
@@ -1007,7 +1066,7 @@ struct Ctx {
                 nd.moves = rr.moves;
                 nd.meta = rr.meta;
             }
-            if (stub) {
+            if constexpr (STUB) {
                 const double value = P.cfg.eval_kind == OTH_EVAL_ROLLOUT ? eval_rollout(lb.x, lb.y, root_init) : eval_stub(lb.x, lb.y);
                 if (!expand(leaf, root_init, nd, lb, false)) break;
                 backup(depth, value);
@@ -1039,6 +1098,7 @@ struct Ctx {
     }
 };
 
+// The hot kernel (external network): expansion, backup, descent.  Moves are only flagged.
 template <int LANES>
 __global__ void __launch_bounds__(kBlock, 8) k_mcts_step(const Params P)
 {
@@ -1048,7 +1108,46 @@ __global__ void __launch_bounds__(kBlock, 8) k_mcts_step(const Params P)
     const int groups = (gridDim.x * kBlock) / LANES;
     for (int s = (blockIdx.x * kBlock + threadIdx.x) / LANES; s < P.cfg.n_slots; s += groups) {
         ctx.slot = s;
-        ctx.run_slot();
+        ctx.template run_slot<false, false>();
+    }
+}
+
+// Device-evaluator build (stubs / rollouts): everything in one kernel, whole simulations per launch.
+template <int LANES>
+__global__ void __launch_bounds__(kBlock) k_mcts_step_stub(const Params P)
+{
+    __shared__ Scratch scratch[kBlock / LANES];
+    cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
+    Ctx<LANES> ctx(tile, P, scratch[threadIdx.x / LANES]);
+    const int groups = (gridDim.x * kBlock) / LANES;
+    for (int s = (blockIdx.x * kBlock + threadIdx.x) / LANES; s < P.cfg.n_slots; s += groups) {
+        ctx.slot = s;
+        ctx.template run_slot<true, true>();
+    }
+}
+
+// Move kernel: one full warp per flagged slot -- policy target, move sampling, trajectory row,
+// breadth-first re-rooting or game hand-off and restart, then the descent that puts the slot's
+// next leaf into the network batch, so a slot never misses an iteration.
+__global__ void __launch_bounds__(kBlock) k_mcts_move(const Params P)
+{
+    __shared__ Scratch scratch[kBlock / 32];
+    cg::thread_block_tile<32> tile = cg::tiled_partition<32>(cg::this_thread_block());
+    Ctx<32> ctx(tile, P, scratch[threadIdx.x / 32]);
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * kBlock) / 32;
+    const int n_sets = (P.cfg.n_slots + 31) / 32;
+    for (int w = (blockIdx.x * kBlock + threadIdx.x) / 32; w < n_sets; w += warps) {
+        const int s0 = w * 32 + lane;
+        unsigned m = __ballot_sync(0xffffffffu, s0 < P.cfg.n_slots && P.move_flags[s0] != 0);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            ctx.slot = w * 32 + b;
+            ctx.template run_slot<true, false>();
+            if (lane == 0) P.move_flags[ctx.slot] = 0;
+            __syncwarp();
+        }
     }
 }
 
@@ -1069,7 +1168,7 @@ __global__ void __launch_bounds__(256) k_mcts_poll(const Params P)
         unsigned x = P.slot_counters[s * CNT_LOCAL + i];
         const oth_mcts_ctl* c = P.ctl + s;
         if (i == OTH_CNT_WAITING) x = c->phase == OTH_PH_WAIT_EVAL;
-        if (i == OTH_CNT_ACTIVE) x = c->top >= 1 && (c->phase == OTH_PH_WAIT_EVAL || c->phase == OTH_PH_RUN);
+        if (i == OTH_CNT_ACTIVE) x = c->top >= 1 && (c->phase == OTH_PH_WAIT_EVAL || c->phase == OTH_PH_RUN || c->phase == OTH_PH_MOVE);
         if (i == OTH_CNT_ERRORS) x = (c->phase == OTH_PH_ERROR || c->error != 0);
         if (i == OTH_CNT_MAX_TOP) x = (unsigned)c->top;
         v = is_max ? (x > v ? x : v) : v + x;
@@ -1268,6 +1367,7 @@ int make_params(const oth_mcts_config* cfg, const oth_mcts_buffers* b, Params* p
     p->counters = (unsigned long long*)b->buf[OTH_BUF_COUNTERS];
     p->slot_counters = (unsigned*)b->buf[OTH_BUF_SLOT_COUNTERS];
     p->hot = (uint4*)b->buf[OTH_BUF_HOT];
+    p->move_flags = (uint8_t*)b->buf[OTH_BUF_MOVE_FLAGS];
     p->priors = nullptr;
     p->values = nullptr;
     p->nn_input = nullptr;
@@ -1319,6 +1419,7 @@ extern "C" int oth_mcts_buffer_bytes(const oth_mcts_config* cfg, int64_t* out)
     out[OTH_BUF_COUNTERS] = 16 * 8;
     out[OTH_BUF_SLOT_COUNTERS] = G * CNT_LOCAL * 4;
     out[OTH_BUF_HOT] = G * 256;
+    out[OTH_BUF_MOVE_FLAGS] = ((G + 63) / 64) * 64;
     return OTH_OK;
 }
 
@@ -1374,7 +1475,16 @@ extern "C" int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers*
     p.priors = priors;
     p.values = values;
     p.nn_input = nn_input;
-    LAUNCH_LANES(k_mcts_step, mcts_grid(cfg), stream, p);
+    if (cfg->eval_kind != OTH_EVAL_EXTERNAL) {
+        LAUNCH_LANES(k_mcts_step_stub, mcts_grid(cfg), stream, p);
+    } else {
+        LAUNCH_LANES(k_mcts_step, mcts_grid(cfg), stream, p);
+        if (cfg->self_play) {
+            const int warps = (cfg->n_slots + 31) / 32;
+            const int blocks = (warps + kBlock / 32 - 1) / (kBlock / 32);
+            k_mcts_move<<<blocks < sm_count() * 4 ? blocks : sm_count() * 4, kBlock, 0, (cudaStream_t)stream>>>(p);
+        }
+    }
     return cuda_status(cudaGetLastError());
 }
 

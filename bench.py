@@ -290,7 +290,10 @@ def run_b200(a):
     torch.cuda.synchronize(dev)
     c1 = eng.counters()
     dk = {k: c1[k] - c0[k] for k in c1}
-    kms = sorted(x.elapsed_time(y) for x, y in zip(ev0, ev1))
+    kms_seq = [x.elapsed_time(y) for x, y in zip(ev0, ev1)]
+    if os.environ.get("OTH_BENCH_DUMP_LAUNCHES"):
+        json.dump(kms_seq, open(os.environ["OTH_BENCH_DUMP_LAUNCHES"], "w"))
+    kms = sorted(kms_seq)
     k_avg = sum(kms) / len(kms)
     alg = algorithmic_bytes(dk, G, iters) / iters
     peak, peak_src = measured_peaks()

@@ -132,6 +132,7 @@ int oth_host_random_read_probe(int64_t buffer_bytes, int32_t chunk_bytes, double
 #define OTH_PH_IDLE 2      /* manual mode: num_simulations done, waiting for oth_mcts_advance */
 #define OTH_PH_DONE 3      /* self-play mode: this slot has played all its games */
 #define OTH_PH_ERROR 4     /* see ctl.error */
+#define OTH_PH_MOVE 5      /* transient inside oth_mcts_step: simulations done, the move kernel takes over */
 
 /* ctl.error bits */
 #define OTH_ERR_NODE_OVERFLOW 1
@@ -208,6 +209,7 @@ enum {
     OTH_BUF_COUNTERS,    /* uint64 [16], see OTH_CNT_*: refreshed by oth_mcts_poll */
     OTH_BUF_SLOT_COUNTERS, /* uint32 [slot][16] cumulative per-slot event counters */
     OTH_BUF_HOT,         /* 256 B [slot]: pending leaf (board, legal set, meta), root header mirror, path[0..52) */
+    OTH_BUF_MOVE_FLAGS,  /* uint8 [slot rounded up to 64]: slots whose move is due (step kernel -> move kernel) */
     OTH_BUF_COUNT
 };
 
