@@ -80,3 +80,35 @@ def collect_self_play_games(policy, args, n_games, *, n_slots=None, device="cuda
     out = SelfPlayRunner(eng, ev, use_graph=use_graph).play()
     eng.raise_on_error()
     return out if return_raw else split_games(out)[:n_games]
+
+
+def collect_self_play_games_distributed(policy, args, n_games_per_rank, *, n_slots=None, dtype=torch.bfloat16, seed=0, version=0):
+    """Sharded ``collect_self_play_games`` (launch with torchrun, one process per GPU, NCCL initialised):
+    rank 0's weights are broadcast, every rank plays its own game ids with no collective on the
+    search path, and the replay tuples are gathered to rank 0, which gets the per-game lists
+    (other ranks get None).  BASELINE config C5 is this with 16 384 slots per rank on 8 GPUs."""
+    import torch.distributed as dist
+    from . import parallel
+    from .Models import fold_for_inference
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    net = policy.to(dev).eval()
+    parallel.broadcast_weights(net, src=0, version=version)
+    n_slots = int(n_slots or min(n_games_per_rank, 4096))
+    gps = -(-n_games_per_rank // n_slots)
+    base, stride = parallel.shard_game_ids(rank, world, n_slots)
+    eng = MctsEngine(n_slots, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=gps, device=dev, seed=seed,
+                     game_id_base=base, game_id_stride=stride)
+    out = SelfPlayRunner(eng, BatchedPolicy(fold_for_inference(net, dtype), dev, torch.float32)).play()
+    eng.raise_on_error()
+    merged = parallel.gather_replay({k: v.to(dev) for k, v in out.items() if k != "states"}, dst=0, device=dev)
+    if merged is None:
+        return None
+    n = merged["values"].numel()
+    states = torch.empty((n, 8, 8), dtype=torch.int8, device=dev)
+    if n:
+        import ctypes as C
+        _lib.check(_lib.lib().oth_unpack_canonical(merged["boards"].contiguous().data_ptr(), states.data_ptr(), n,
+                                                   C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    merged["states"] = states
+    return split_games({k: v.cpu() for k, v in merged.items()})

@@ -62,6 +62,14 @@ def main():
             assert a[gid][3] == b[gid][3]
         print(f"dist check ok: world={world}, {len(a)} games, {int(merged['values'].numel())} positions gathered to rank 0, "
               f"identical to the single-GPU run", flush=True)
+    # 3. the packaged entry point with a real network
+    from alphazero_othello_b200.self_play_worker import collect_self_play_games_distributed
+    args = {"c_puct": 2.0, "num_simulations": 8, "dirichlet_alpha": 1.0, "dirichlet_epsilon": 0.3, "mcts_temperature": 1.0,
+            "num_exploratory_moves": 35, "lambda": 0.98}
+    games = collect_self_play_games_distributed(net, args, 32, n_slots=32)
+    if rank == 0:
+        assert len(games) == 32 * world and all(9 <= len(g) <= 128 and abs(g[0][1].sum() - 1) < 1e-5 for g in games)
+        print(f"collect_self_play_games_distributed ok: {len(games)} games on rank 0", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
