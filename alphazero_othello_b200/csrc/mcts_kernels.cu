@@ -1,11 +1,13 @@
 // Batched MCTS self-play engine for B200 (sm_100a).
 //
-// One group of LANES threads (a warp by default) owns one game slot.  The tree
-// of a slot lives in two flat arenas in HBM (32-byte node records + 16-byte
-// boards); children of a node are contiguous and in ascending action order,
-// so PUCT selection is one coalesced 2x128-bit load per lane and a shuffle
-// arg-max.  Re-rooting (MCTS.make_move) compacts the kept subtree into the
-// other arena, breadth first.
+// One group of LANES threads (8 by default; 16 / 32 selectable) owns one game
+// slot.  The tree of a slot lives in two flat arenas in HBM (32-byte node
+// records + 16-byte boards); children of a node are contiguous and in
+// ascending action order, so PUCT selection is one 2x128-bit load per lane and
+// a two-instruction warp-reduce arg-max.  k_mcts_step (hot: expand, backup,
+// descend) hands slots whose move is due to k_mcts_move (policy target, move
+// sampling, re-rooting = breadth-first compaction of the kept subtree into the
+// other arena, game hand-off), both launched by one oth_mcts_step call.
 //
 // Semantics restated from the reference (num_threads = 1):
 //   Node / PUCT / expand / backup    MCTS_model.py:46-169
