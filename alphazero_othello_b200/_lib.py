@@ -71,6 +71,7 @@ _SIGS = {
     "oth_error_string": (C.c_char_p, [C.c_int]),
     "oth_last_cuda_error": (C.c_char_p, []),
     "oth_device_count": (C.c_int, []),
+    "oth_set_l2_fetch_granularity": (C.c_int, [C.c_int32]),
     "oth_legal_moves": (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]),
     "oth_step": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, C.c_void_p]),
     "oth_rollout": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

@@ -461,6 +461,14 @@ extern "C" const char* oth_error_string(int code)
 
 extern "C" const char* oth_last_cuda_error(void) { return g_cuda_err; }
 
+// Device-wide hint (cudaLimitMaxL2FetchGranularity): 32 suits isolated 32-byte tree records,
+// the default 64 / 128 suits streaming kernels.  Exposed so hosts can experiment.
+extern "C" int oth_set_l2_fetch_granularity(int32_t bytes)
+{
+    if (bytes != 32 && bytes != 64 && bytes != 128) return OTH_E_ARG;
+    return cuda_status(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+}
+
 extern "C" int oth_device_count(void)
 {
     int n = 0;

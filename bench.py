@@ -161,6 +161,9 @@ def run_b200(a):
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+    if os.environ.get("OTH_L2_FETCH"):  # experiment: cudaLimitMaxL2FetchGranularity (0x05) = 32 / 64 / 128
+        rc = _lib.lib().oth_set_l2_fetch_granularity(int(os.environ["OTH_L2_FETCH"]))
+        print("cudaDeviceSetLimit(L2 fetch granularity)", os.environ["OTH_L2_FETCH"], "->", rc, file=sys.stderr)
     desc, kind, G, sims = WORKLOADS[a.workload]
     if a.games:
         G = a.games

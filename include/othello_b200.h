@@ -54,6 +54,8 @@ int oth_abi_version(void);
 const char* oth_error_string(int code);
 const char* oth_last_cuda_error(void);
 int oth_device_count(void);
+/* cudaLimitMaxL2FetchGranularity for the current device: 32, 64 or 128 bytes (a hint). */
+int oth_set_l2_fetch_granularity(int32_t bytes);
 
 /* ------------------------------------------------------------------ env -- */
 
