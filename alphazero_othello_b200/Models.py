@@ -165,8 +165,21 @@ class _StemGemm(nn.Module):
         return y.view(B, 8, 8, self.cout).permute(0, 3, 1, 2)  # NHWC memory == channels_last [B,C,8,8]
 
 
+def _pad_rows(w, b, mult=64):
+    """Zero-pad a linear layer's output rows to a multiple of `mult`: odd sizes (65, 129, 1) push
+    cuBLAS onto slow legacy kernels."""
+    n = w.size(0)
+    m = ((n + mult - 1) // mult) * mult
+    wp = torch.zeros(m, w.size(1), dtype=w.dtype, device=w.device)
+    bp = torch.zeros(m, dtype=b.dtype, device=b.device)
+    wp[:n], bp[:n] = w, b
+    return wp, bp
+
+
 class FoldedNet(nn.Module):
-    """Inference-only twin of FastOthelloNet / AlphaZeroNet (same function up to dtype rounding)."""
+    """Inference-only twin of FastOthelloNet / AlphaZeroNet (same function up to dtype rounding):
+    BatchNorm folded, channels-last activations, and both heads as ONE GEMM over the NHWC-flattened
+    trunk output (policy logits | value hidden) followed by the tiny value output layer."""
 
     def __init__(self, net, dtype=torch.bfloat16):
         super().__init__()
@@ -174,28 +187,42 @@ class FoldedNet(nn.Module):
         self.kind = "big" if isinstance(net, AlphaZeroNet) or hasattr(net, "pol_conv") else "small"
         mk = lambda c, bn: _FusedConv(*_fold(c, bn), dtype)
         stem = (lambda c, bn: _StemGemm(*_fold(c, bn), dtype)) if dtype != torch.float32 else mk
+        f32 = lambda t: t.detach().float()
         if self.kind == "small":
             self.stem = stem(net.initial_conv[0], net.initial_conv[1])
             self.blocks = nn.ModuleList([nn.ModuleList([mk(net.res_block.conv1, net.res_block.bn1),
                                                         mk(net.res_block.conv2, net.res_block.bn2)])])
             self.tail = mk(net.conv_add[0], net.conv_add[1])
-            # one GEMM for both heads: [policy(65) | value hidden(64)] over the NHWC-flattened features
-            wp, wv = net.fc_policy.weight.detach().float(), net.fc_value1.weight.detach().float()
+            wp, wv = f32(net.fc_policy.weight), f32(net.fc_value1.weight)
             w = torch.cat([wp, wv], 0).view(-1, 64, 8, 8).permute(0, 2, 3, 1).reshape(wp.size(0) + wv.size(0), -1)
-            self.register_buffer("head_w", w.to(dtype).contiguous())
-            self.register_buffer("head_b", torch.cat([net.fc_policy.bias, net.fc_value1.bias]).detach().to(dtype))
-            self.register_buffer("v2_w", net.fc_value2.weight.detach().to(dtype))
-            self.register_buffer("v2_b", net.fc_value2.bias.detach().to(dtype))
+            hb = torch.cat([f32(net.fc_policy.bias), f32(net.fc_value1.bias)])
+            self.n_hidden = wv.size(0)
+            v2w, v2b = f32(net.fc_value2.weight), f32(net.fc_value2.bias)
         else:
             self.stem = stem(net.conv0, net.bn0)
             self.blocks = nn.ModuleList([nn.ModuleList([mk(b.conv1, b.bn1), mk(b.conv2, b.bn2)]) for b in net.res])
-            # both 1x1 head convolutions as one 3-channel convolution
+            # both 1x1 head convolutions as one 3-channel convolution (2 policy planes, 1 value plane) ...
             pw, pb = _fold(net.pol_conv, net.pol_bn)
             vw, vb = _fold(net.val_conv, net.val_bn)
             self.heads = _FusedConv(torch.cat([pw, vw], 0), torch.cat([pb, vb], 0), dtype)
-            self.pol_fc = net.pol_fc
-            self.val_fc1, self.val_fc2 = net.val_fc1, net.val_fc2
+            # ... and both first linear layers as one matrix over its NHWC flattening [hw*3 + c]
+            wpol, wval = f32(net.pol_fc.weight), f32(net.val_fc1.weight)  # [65, 2*64] (c*64+hw), [256, 64] (hw)
+            no, nh = wpol.size(0), wval.size(0)
+            w = torch.zeros(no + nh, 64, 3, device=wpol.device)
+            w[:no, :, 0:2] = wpol.view(no, 2, 64).permute(0, 2, 1)
+            w[no:, :, 2] = wval
+            w = w.view(no + nh, 192)
+            hb = torch.cat([f32(net.pol_fc.bias), f32(net.val_fc1.bias)])
+            self.n_hidden = nh
+            v2w, v2b = f32(net.val_fc2.weight), f32(net.val_fc2.bias)
+        w, hb = _pad_rows(w, hb)
+        v2w, v2b = _pad_rows(v2w, v2b, 8)
+        self.register_buffer("head_w", w.to(dtype).contiguous())
+        self.register_buffer("head_b", hb.to(dtype))
+        self.register_buffer("v2_w", v2w.to(dtype).contiguous())
+        self.register_buffer("v2_b", v2b.to(dtype))
         self.n_actions = net.action_size
+        self.raw_outputs = False
 
     @torch.no_grad()
     def forward(self, x):
@@ -206,16 +233,13 @@ class FoldedNet(nn.Module):
             h = h.contiguous(memory_format=torch.channels_last)
         for c1, c2 in self.blocks:
             h = c2(c1(h), residual=h)
-        if self.kind == "small":
-            h = self.tail(h)
-            y = F.linear(h.permute(0, 2, 3, 1).reshape(h.size(0), -1), self.head_w, self.head_b)
-            logits = y[:, :self.n_actions]
-            v = torch.tanh(F.linear(F.relu(y[:, self.n_actions:]), self.v2_w, self.v2_b))
-            return logits.float(), v.float()
-        y = self.heads(h).float()  # [B,3,8,8]: two policy planes, one value plane (ReLU applied)
-        p = self.pol_fc(y[:, :2].reshape(y.size(0), -1))
-        v = torch.tanh(self.val_fc2(F.relu(self.val_fc1(y[:, 2].reshape(y.size(0), -1)))))
-        return p, v
+        h = self.tail(h) if self.kind == "small" else self.heads(h)
+        y = F.linear(h.permute(0, 2, 3, 1).reshape(h.size(0), -1), self.head_w, self.head_b)  # NHWC flattening: a view
+        na, nh = self.n_actions, self.n_hidden
+        v = F.linear(F.relu(y[:, na:na + nh]), self.v2_w, self.v2_b)[:, :1]
+        if getattr(self, "raw_outputs", False):  # engine path: (logits, value pre-activation) in the compute dtype,
+            return y[:, :na], v                  # softmax / tanh are applied by BatchedPolicy with fp32 outputs
+        return y[:, :na].float(), torch.tanh(v.float())
 
 
 @torch.no_grad()

@@ -208,6 +208,15 @@ class BatchedPolicy:
 
     @torch.no_grad()
     def __call__(self, x, priors_out, values_out):
+        if getattr(self.policy, "raw_outputs", None) is not None:
+            # network twin: logits / value pre-activation straight from the head GEMMs; one softmax kernel
+            # (cast fused) and one cast + one tanh for the values
+            self.policy.raw_outputs = True
+            logits, v = self.policy(x)
+            torch.softmax(logits, dim=-1, dtype=torch.float32, out=priors_out)
+            values_out.copy_(v.reshape(-1))
+            values_out.tanh_()
+            return
         if self.dtype != torch.float32:
             with torch.autocast("cuda", dtype=self.dtype):
                 logits, value = self.policy(x)
