@@ -1093,6 +1093,7 @@ struct Ctx {
                 S.hot.leaf_meta = nd.meta;
             }
         }
+        count_max(OTH_CNT_MAX_TOP, (unsigned)c.top);  // arena high-water mark of this slot
         if (lane == 0) P.ctl[slot] = c;
         store_hot(c.phase == OTH_PH_WAIT_EVAL ? c.path_len : 0);
         store_counters();
@@ -1172,7 +1173,6 @@ __global__ void __launch_bounds__(256) k_mcts_poll(const Params P)
         if (i == OTH_CNT_WAITING) x = c->phase == OTH_PH_WAIT_EVAL;
         if (i == OTH_CNT_ACTIVE) x = c->top >= 1 && (c->phase == OTH_PH_WAIT_EVAL || c->phase == OTH_PH_RUN || c->phase == OTH_PH_MOVE);
         if (i == OTH_CNT_ERRORS) x = (c->phase == OTH_PH_ERROR || c->error != 0);
-        if (i == OTH_CNT_MAX_TOP) x = (unsigned)c->top;
         v = is_max ? (x > v ? x : v) : v + x;
     }
     if (v) {

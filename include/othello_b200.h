@@ -224,7 +224,7 @@ enum {
     OTH_CNT_OUT_GAMES,    /* finished-game descriptors since the last drain */
     OTH_CNT_MOVES,        /* moves played */
     OTH_CNT_ERRORS,       /* slots in error (gauge, oth_mcts_poll) */
-    OTH_CNT_MAX_TOP,      /* fullest arena (gauge, oth_mcts_poll) */
+    OTH_CNT_MAX_TOP,      /* arena high-water mark over all slots */
     OTH_CNT_MAX_DEPTH,    /* deepest path seen */
     OTH_CNT_NODES,        /* nodes created */
     OTH_CNT_COPIED,       /* nodes copied by re-rooting */

@@ -271,3 +271,36 @@ def test_rollout_evaluator_policy_none_vs_oracle(lanes):
         e.advance(torch.tensor(acts, dtype=torch.int32, device="cuda"))
         e.raise_on_error()
     assert len({tuple(st["counts"][i]) for i in range(n)}) > 1  # different game ids -> different playouts
+
+
+def test_output_ring_and_path_overflow_fail_loudly():
+    from alphazero_othello_b200 import _lib
+    args = {"c_puct": 2.0, "num_simulations": 6, "dirichlet_epsilon": 0.0, "mcts_temperature": 1.0, "num_exploratory_moves": 60}
+    e = _selfplay_engine(args, 8, 4, False, 1, out_pos_cap=40, out_game_cap=8)  # a game has ~60 positions
+    with pytest.raises(_lib.OthelloB200Error, match="output ring overflow"):
+        _run_to_done(e, 4000)
+    args = {"c_puct": 2.0, "num_simulations": 400, "dirichlet_epsilon": 0.0}
+    e = _selfplay_engine(args, 8, 2, False, 1, path_cap=3)
+    with pytest.raises(_lib.OthelloB200Error, match="path overflow"):
+        _run_to_done(e, 4000)
+
+
+def test_many_simulations_deep_tree_matches_oracle():
+    """400 simulations per move (the C4 setting) on a few games: deep paths, big arenas, many re-roots."""
+    import oracle as O
+    from alphazero_othello_b200.engine import split_games
+    args = {"c_puct": 2.0, "num_simulations": 400, "dirichlet_alpha": 1.0, "dirichlet_epsilon": 0.3,
+            "mcts_temperature": 1.0, "num_exploratory_moves": 35, "lambda": 0.98}
+    n = 6
+    e = _selfplay_engine(args, 8, n, False, 7, seed=31)
+    _run_to_done(e, 200000)
+    noise = e.noise.cpu().numpy(); um = e.u_move.cpu().numpy(); ut = e.u_tie.cpu().numpy()
+    c = e.counters()
+    games = split_games(e.drain())
+    assert c["max_depth"] >= 8 and c["max_top"] > 3000
+    for g in range(n):
+        ref = O.self_play(args, O.Evaluator(stub=O.STUB_H, salt=7), noise[g], um[g], ut[g])
+        traj = games[g]
+        assert len(traj) == len(ref["values"])
+        assert np.array_equal(np.stack([t[1] for t in traj]), ref["pis"]), g
+        assert np.array_equal(np.array([t[2] for t in traj]), ref["values"]), g
