@@ -19,48 +19,59 @@ from .envs.othello import OthelloGameNew as OthelloGame
 
 
 def get_training_data(trajectory, winning_player, lambd=1.0):
-    """Backward lambda-return over one game (self_play_worker.py:8-35); the batched engine
-    computes the same recurrence in-kernel (emit_game in csrc/mcts_kernels.cu)."""
-    out = [None] * len(trajectory)
-    g_next, next_player = None, None
-    for t in range(len(trajectory) - 1, -1, -1):
+    """Value targets for one finished game: the backward lambda-return of self_play_worker.py:8-35.
+    ``trajectory`` rows are ``(state, pi, player, root_value)``; returns ``(state, pi, G_t)`` rows.
+    The batched engine evaluates the same recurrence in-kernel (emit_game, csrc/mcts_kernels.cu)."""
+    def outcome(p):
+        return 0.0 if winning_player == 0 else (1.0 if p == winning_player else -1.0)
+
+    rows = [None] * len(trajectory)
+    later = None  # (G_{t+1}, player_{t+1})
+    for t in reversed(range(len(trajectory))):
         state, pi, player, v_root = trajectory[t]
-        z = 0.0 if winning_player == 0 else (1.0 if player == winning_player else -1.0)
-        if g_next is None:
-            g = z
+        if later is None:
+            g = outcome(player)
         else:
-            sign = 1.0 if player == next_player else -1.0
+            g_next, p_next = later
+            sign = 1.0 if player == p_next else -1.0
             g = (1.0 - lambd) * v_root + lambd * sign * g_next
-        out[t] = (state, pi, g)
-        g_next, next_player = g, player
-    return out
+        rows[t] = (state, pi, g)
+        later = (g, player)
+    return rows
+
+
+def _rebuild_policy(policy_state):
+    cls, cfg, weights = policy_state
+    net = cls(**cfg)
+    net.load_state_dict(weights)
+    net.eval()
+    return net
 
 
 @torch.no_grad()
 def one_self_play(args_tuple):
+    """One complete game on the GPU-resident tree, behind the reference's worker signature
+    (self_play_worker.py:38-88): ``(board_size, args, (policy_class, policy_config, state_dict),
+    inference_cache) -> [(state int8[8,8], pi float32[65], value float), ...]``.  np.random is
+    consumed in the reference's order (root noise, tie picks, one ``choice(65, p)`` per ply)."""
     board_size, args, policy_state, inference_cache = args_tuple
     env = OthelloGame(board_size)
-    policy_class, policy_config, policy_state_dict = policy_state
-    policy = policy_class(**policy_config)
-    policy.load_state_dict(policy_state_dict)
-    policy.eval()
-    mcts = MCTS(env, args, policy, dirichlet_alpha=args["dirichlet_alpha"], dirichlet_epsilon=args["dirichlet_epsilon"],
-                inference_cache=inference_cache)
-    trajectory = []
-    state = env.get_initial_state()
-    player, is_terminal = 1, False
-    while not is_terminal:
-        temperature = args["mcts_temperature"] if len(trajectory) < args["num_exploratory_moves"] else 0.0
-        action_probs = mcts.policy_improve_step(state, player, temp=temperature)
-        trajectory.append((state.copy() * player, action_probs.copy(), player, mcts.root.value))
-        action = np.random.choice(env.action_size, p=action_probs)
-        mcts.make_move(action)
-        state = env.get_next_state(state, action, player)
-        reward, is_terminal = env.get_value_and_terminated(state, action, player)
-        if is_terminal:
-            winner = player if reward > 0 else (env.get_opponent(player) if reward < 0 else 0)
-            return get_training_data(trajectory, winner, args["lambda"])
-        player = env.get_opponent(player)
+    search = MCTS(env, args, _rebuild_policy(policy_state), dirichlet_alpha=args["dirichlet_alpha"],
+                  dirichlet_epsilon=args["dirichlet_epsilon"], inference_cache=inference_cache)
+    history = []
+    board, mover = env.get_initial_state(), 1
+    while True:
+        exploring = len(history) < args["num_exploratory_moves"]
+        pi = search.policy_improve_step(board, mover, temp=args["mcts_temperature"] if exploring else 0.0)
+        history.append((board.copy() * mover, pi.copy(), mover, search.root.value))
+        move = np.random.choice(env.action_size, p=pi)
+        search.make_move(move)
+        board = env.get_next_state(board, move, mover)
+        reward, over = env.get_value_and_terminated(board, move, mover)
+        if over:
+            winner = 0 if reward == 0 else (mover if reward > 0 else env.get_opponent(mover))
+            return get_training_data(history, winner, args["lambda"])
+        mover = env.get_opponent(mover)
 
 
 def collect_self_play_games(policy, args, n_games, *, n_slots=None, device="cuda:0", dtype=torch.bfloat16, seed=0,
