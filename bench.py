@@ -324,7 +324,10 @@ def run_b200(a):
             "config": {"workload": f"{a.workload}: {desc}", "net": kind, "games_per_gpu": G, "sims_per_move": sims,
                        "iters_per_step": iters, "lanes": a.lanes, "cuda_graph": not a.no_graph,
                        "l2": f"tree arenas {eng.buf_bytes[0] + eng.buf_bytes[1] >> 20} MiB per GPU >> 126 MB L2 (inputs larger than L2)",
-                       "sharding": "games by id, no collective on the search path"},
+                       "sharding": "games by id, no collective on the search path",
+                       "roofline_timing": "CUDA events around every oth_mcts_step launch (k_mcts_step + k_mcts_move) in an un-graphed "
+                                          "pass of iters_per_step iterations of the same pipeline right after the timed region "
+                                          "(events cannot be recorded inside the replayed graph)"},
             "positions_per_s": moves_total / (ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": "sims/s", "h2d_bytes_per_step": io["h2d"] // a.steps,
                     "d2h_bytes_per_step": io["d2h"] // a.steps, "ms_per_step": ms2 / a.steps,
