@@ -1117,7 +1117,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_mcts_step(const Params P)
 
 // Device-evaluator build (stubs / rollouts): everything in one kernel, whole simulations per launch.
 template <int LANES>
-__global__ void __launch_bounds__(kBlock) k_mcts_step_stub(const Params P)
+__global__ void __launch_bounds__(kBlock, 4) k_mcts_step_stub(const Params P)
 {
     __shared__ Scratch scratch[kBlock / LANES];
     cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
