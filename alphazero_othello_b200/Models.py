@@ -201,17 +201,25 @@ class FoldedNet(nn.Module):
         else:
             self.stem = stem(net.conv0, net.bn0)
             self.blocks = nn.ModuleList([nn.ModuleList([mk(b.conv1, b.bn1), mk(b.conv2, b.bn2)]) for b in net.res])
-            # both 1x1 head convolutions as one 3-channel convolution (2 policy planes, 1 value plane) ...
+            # both 1x1 head convolutions (2 policy planes, 1 value plane) as one GEMM over the NHWC trunk
+            # output: [B*64, C] x [C, 16] (3 real columns, zero-padded) with the bias+ReLU epilogue fused ...
             pw, pb = _fold(net.pol_conv, net.pol_bn)
             vw, vb = _fold(net.val_conv, net.val_bn)
-            self.heads = _FusedConv(torch.cat([pw, vw], 0), torch.cat([pb, vb], 0), dtype)
-            # ... and both first linear layers as one matrix over its NHWC flattening [hw*3 + c]
+            C_in = pw.size(1)
+            hw1 = torch.zeros(C_in, 16, device=pw.device)
+            hw1[:, 0:2] = pw.view(2, C_in).t()
+            hw1[:, 2] = vw.view(C_in)
+            hb1 = torch.zeros(16, device=pw.device)
+            hb1[0:2], hb1[2] = pb, vb[0]
+            self.register_buffer("heads_w", hw1.to(dtype).contiguous())
+            self.register_buffer("heads_b", hb1.to(dtype))
+            # ... and both first linear layers as one matrix over its flattening [hw*16 + c]
             wpol, wval = f32(net.pol_fc.weight), f32(net.val_fc1.weight)  # [65, 2*64] (c*64+hw), [256, 64] (hw)
             no, nh = wpol.size(0), wval.size(0)
-            w = torch.zeros(no + nh, 64, 3, device=wpol.device)
+            w = torch.zeros(no + nh, 64, 16, device=wpol.device)
             w[:no, :, 0:2] = wpol.view(no, 2, 64).permute(0, 2, 1)
             w[no:, :, 2] = wval
-            w = w.view(no + nh, 192)
+            w = w.view(no + nh, 64 * 16)
             hb = torch.cat([f32(net.pol_fc.bias), f32(net.val_fc1.bias)])
             self.n_hidden = nh
             v2w, v2b = f32(net.val_fc2.weight), f32(net.val_fc2.bias)
@@ -233,8 +241,13 @@ class FoldedNet(nn.Module):
             h = h.contiguous(memory_format=torch.channels_last)
         for c1, c2 in self.blocks:
             h = c2(c1(h), residual=h)
-        h = self.tail(h) if self.kind == "small" else self.heads(h)
-        y = F.linear(h.permute(0, 2, 3, 1).reshape(h.size(0), -1), self.head_w, self.head_b)  # NHWC flattening: a view
+        B = h.size(0)
+        if self.kind == "small":
+            feat = self.tail(h).permute(0, 2, 3, 1).reshape(B, -1)  # NHWC flattening: a view
+        else:
+            hf = h.permute(0, 2, 3, 1).reshape(B * 64, -1)  # [B*64, C] view of the channels-last trunk output
+            feat = torch._addmm_activation(self.heads_b, hf, self.heads_w, use_gelu=False).view(B, -1)
+        y = F.linear(feat, self.head_w, self.head_b)
         na, nh = self.n_actions, self.n_hidden
         v = F.linear(F.relu(y[:, na:na + nh]), self.v2_w, self.v2_b)[:, :1]
         if getattr(self, "raw_outputs", False):  # engine path: (logits, value pre-activation) in the compute dtype,
