@@ -154,13 +154,19 @@ class _StemGemm(nn.Module):
         self.register_buffer("b", b.to(dtype))
         self.cout = cout
 
-    def forward(self, x):  # x [B,1,8,8] in self.wt.dtype
+    def forward(self, x):  # x [B,1,8,8]: float32 (engine path) or already in the compute dtype
         B = x.size(0)
         cols = getattr(self, "_cols", None)
-        if cols is None or cols.size(0) != B or cols.dtype != x.dtype or cols.device != x.device:
-            cols = self._cols = torch.zeros(B, 8, 8, 16, dtype=x.dtype, device=x.device)  # K columns 9..15 stay zero
-        taps = F.pad(x[:, 0], (1, 1, 1, 1)).unfold(1, 3, 1).unfold(2, 3, 1)  # [B,8,8,3,3] view, no copy
-        cols[..., :9].unflatten(-1, (3, 3)).copy_(taps)  # one strided copy = im2col
+        if cols is None or cols.size(0) != B or cols.dtype != self.wt.dtype or cols.device != x.device:
+            cols = self._cols = torch.zeros(B, 8, 8, 16, dtype=self.wt.dtype, device=x.device)  # K columns 9..15 stay zero
+        if x.dtype == torch.float32 and cols.dtype == torch.bfloat16 and x.is_contiguous():
+            import ctypes as C
+            from . import _lib
+            _lib.check(_lib.lib().oth_nn_stem_im2col_bf16(x.data_ptr(), cols.data_ptr(), B,
+                                                          C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+        else:
+            taps = F.pad(x[:, 0].to(cols.dtype), (1, 1, 1, 1)).unfold(1, 3, 1).unfold(2, 3, 1)  # [B,8,8,3,3] view
+            cols[..., :9].unflatten(-1, (3, 3)).copy_(taps)  # one strided copy = im2col
         y = torch._addmm_activation(self.b, cols.view(B * 64, 16), self.wt, use_gelu=False)  # relu epilogue
         return y.view(B, 8, 8, self.cout).permute(0, 3, 1, 2)  # NHWC memory == channels_last [B,C,8,8]
 
@@ -236,7 +242,7 @@ class FoldedNet(nn.Module):
     def forward(self, x):
         if x.dim() == 3:
             x = x.unsqueeze(1)
-        h = self.stem(x.to(self.dtype))
+        h = self.stem(x if isinstance(self.stem, _StemGemm) else x.to(self.dtype))
         if not h.is_contiguous(memory_format=torch.channels_last):
             h = h.contiguous(memory_format=torch.channels_last)
         for c1, c2 in self.blocks:

@@ -101,6 +101,7 @@ _SIGS = {
     "oth_unpack_canonical": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "oth_replay_aggregate_workspace_bytes": (C.c_int, [C.c_int64, C.c_void_p]),
     "oth_replay_aggregate": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_int64] + [C.c_void_p] * 7),
+    "oth_nn_stem_im2col_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "oth_nn_bias_add_relu_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
 }
 

@@ -312,6 +312,44 @@ __global__ void __launch_bounds__(256) k_bias_add_relu_bf16(uint4* __restrict__ 
     }
 }
 
+// Network-boundary im2col for the 1-channel 3x3 stem: float32 planes [n,64] -> bf16 [n,64,16]
+// (9 taps in (dy,dx) order, zero padding at the border, columns 9..15 zero), one thread per square.
+__global__ void __launch_bounds__(256) k_stem_im2col_bf16(const float* __restrict__ planes, uint4* __restrict__ cols, int64_t n64)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n64; t += stride) {
+        const int sq = (int)(t & 63), r = sq >> 3, c = sq & 7;
+        const float* p = planes + (t - sq);
+        float v[9];
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++) {
+                const int rr = r + dy, cc = c + dx;
+                v[(dy + 1) * 3 + dx + 1] = (rr >= 0 && rr < 8 && cc >= 0 && cc < 8) ? p[rr * 8 + cc] : 0.0f;
+            }
+        uint4 a, b;
+        __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
+        __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&b);
+        pa[0] = __floats2bfloat162_rn(v[0], v[1]);
+        pa[1] = __floats2bfloat162_rn(v[2], v[3]);
+        pa[2] = __floats2bfloat162_rn(v[4], v[5]);
+        pa[3] = __floats2bfloat162_rn(v[6], v[7]);
+        pb[0] = __floats2bfloat162_rn(v[8], 0.0f);
+        pb[1] = pb[2] = pb[3] = __floats2bfloat162_rn(0.0f, 0.0f);
+        cols[2 * t] = a;
+        cols[2 * t + 1] = b;
+    }
+}
+
+extern "C" int oth_nn_stem_im2col_bf16(const float* planes, void* cols, int64_t n, void* stream)
+{
+    if (n < 0 || (n > 0 && (!planes || !cols)) || ((uintptr_t)cols & 15)) return OTH_E_ARG;
+    if (n == 0) return OTH_OK;
+    k_stem_im2col_bf16<<<grid_for(n * 64, 256), 256, 0, (cudaStream_t)stream>>>(planes, (uint4*)cols, n * 64);
+    return cuda_status(cudaGetLastError());
+}
+
 extern "C" int oth_nn_bias_add_relu_bf16(void* x, const void* res, const void* bias, int64_t n, int32_t channels, void* stream)
 {
     if (n < 0 || channels <= 0 || (channels % 8) || (n % 8) || !x || !res || !bias) return OTH_E_ARG;

@@ -333,8 +333,9 @@ def run_b200(a):
                     "d2h_bytes_per_step": io["d2h"] // a.steps, "ms_per_step": ms2 / a.steps,
                     "includes": "weights H2D from pinned host (+NCCL broadcast if sharded), BN re-fold, "
                                 "D2H of policy targets/root values and finished games' replay tuples (+gather to rank 0)"},
-            # this repo's kernels per iteration: k_mcts_step + one k_bias_add_relu_bf16 per residual block of the network twin
-            "gpu_launches": a.steps * iters * (1 + (5 if kind == "big" else 1)),
+            # this repo's kernels per iteration: k_mcts_step, k_mcts_move, k_stem_im2col_bf16 and one
+            # k_bias_add_relu_bf16 per residual block of the network twin
+            "gpu_launches": a.steps * iters * (3 + (5 if kind == "big" else 1)),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": f"k_mcts_step<{a.lanes}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -308,6 +308,11 @@ int oth_replay_aggregate(const uint64_t* boards, const float* pis, const double*
  * n = element count (multiple of 8), channels multiple of 8, 16-byte aligned pointers. */
 int oth_nn_bias_add_relu_bf16(void* x, const void* res, const void* bias, int64_t n, int32_t channels, void* stream);
 
+/* Network boundary helper: im2col of the leaf planes for the 1-input-channel 3x3 stem convolution
+ * (Models.py:105-107 / :179): float32 [n,64] -> bf16 [n,64,16] (9 taps + 7 zero columns), so the
+ * stem runs as one GEMM with a fused bias+ReLU epilogue and writes channels-last output. */
+int oth_nn_stem_im2col_bf16(const float* planes, void* cols, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
