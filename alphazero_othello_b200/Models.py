@@ -236,10 +236,10 @@ class FoldedNet(nn.Module):
         self.register_buffer("v2_w", v2w.to(dtype).contiguous())
         self.register_buffer("v2_b", v2b.to(dtype))
         self.n_actions = net.action_size
-        self.raw_outputs = False
+        self.supports_raw = True
 
     @torch.no_grad()
-    def forward(self, x):
+    def forward(self, x, raw=False):
         if x.dim() == 3:
             x = x.unsqueeze(1)
         h = self.stem(x if isinstance(self.stem, _StemGemm) else x.to(self.dtype))
@@ -256,8 +256,8 @@ class FoldedNet(nn.Module):
         y = F.linear(feat, self.head_w, self.head_b)
         na, nh = self.n_actions, self.n_hidden
         v = F.linear(F.relu(y[:, na:na + nh]), self.v2_w, self.v2_b)[:, :1]
-        if getattr(self, "raw_outputs", False):  # engine path: (logits, value pre-activation) in the compute dtype,
-            return y[:, :na], v                  # softmax / tanh are applied by BatchedPolicy with fp32 outputs
+        if raw:  # engine path: (logits, value pre-activation) views in the compute dtype; softmax / tanh are
+            return y[:, :na], v  # applied downstream (fused into oth_mcts_step_fused, or by BatchedPolicy)
         return y[:, :na].float(), torch.tanh(v.float())
 
 

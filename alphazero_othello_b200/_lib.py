@@ -95,6 +95,8 @@ _SIGS = {
     "oth_mcts_set_roots_masked": (C.c_int, [C.c_void_p] * 7),
     "oth_mcts_begin_search_masked": (C.c_int, [C.c_void_p] * 4),
     "oth_mcts_step": (C.c_int, [C.c_void_p] * 6),
+    "oth_mcts_step_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "oth_mcts_advance": (C.c_int, [C.c_void_p] * 4),
     "oth_mcts_poll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "oth_mcts_root_stats": (C.c_int, [C.c_void_p] * 9),

@@ -18,6 +18,7 @@
 // Compiled with --fmad=false; the rounding-critical steps also use the
 // explicit *_rn intrinsics.
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -116,6 +117,12 @@ struct Params {
     uint8_t* move_flags;      // [slot] set by the step kernel when a slot's move is due (k_mcts_move clears it)
     const float* priors;
     const float* values;
+    // fused network tail (oth_mcts_step_fused): raw logits / value pre-activations, row strides in elements
+    const void* logits;
+    const void* vpre;
+    int logits_stride, vpre_stride, raw_bf16;
+    float* priors_out;  // optional: the softmax / tanh the kernel applied, for record & replay
+    float* values_out;
     float* nn_input;
     float c_puct_f32;
 };
@@ -966,7 +973,8 @@ struct Ctx {
     //       hand-off).  The hot kernel (MOVE = false) only flags such slots; k_mcts_move picks
     //       them up in the same oth_mcts_step call with a full warp per slot.
     // STUB: device evaluators compiled in (search-only / test builds of the kernel).
-    template <bool MOVE, bool STUB>
+    // FUSED: the network's softmax (Models.py:24-25) and tanh are applied here, on raw logits.
+    template <bool MOVE, bool STUB, bool FUSED = false>
     __device__ void run_slot()
     {
         // (1) everything that depends only on the slot index is requested at once:
@@ -976,13 +984,33 @@ struct Ctx {
         float pv[NPL];
         float nn_value = 0.0f;
         if (!stub && !(MOVE && !STUB)) {
-            const float* pr = P.priors + (size_t)slot * OTH_NUM_ACTIONS;
+            if constexpr (FUSED) {
+                if (P.raw_bf16) {
+                    const __nv_bfloat16* lg = (const __nv_bfloat16*)P.logits + (size_t)slot * P.logits_stride;
 #pragma unroll
-            for (int k = 0; k < NPL; k++) {
-                const int a = lane + k * LANES;
-                pv[k] = a < OTH_NUM_ACTIONS ? pr[a] : 0.0f;
+                    for (int k = 0; k < NPL; k++) {
+                        const int a = lane + k * LANES;
+                        pv[k] = a < OTH_NUM_ACTIONS ? __bfloat162float(lg[a]) : -INFINITY;
+                    }
+                    nn_value = __bfloat162float(((const __nv_bfloat16*)P.vpre)[(size_t)slot * P.vpre_stride]);
+                } else {
+                    const float* lg = (const float*)P.logits + (size_t)slot * P.logits_stride;
+#pragma unroll
+                    for (int k = 0; k < NPL; k++) {
+                        const int a = lane + k * LANES;
+                        pv[k] = a < OTH_NUM_ACTIONS ? lg[a] : -INFINITY;
+                    }
+                    nn_value = ((const float*)P.vpre)[(size_t)slot * P.vpre_stride];
+                }
+            } else {
+                const float* pr = P.priors + (size_t)slot * OTH_NUM_ACTIONS;
+#pragma unroll
+                for (int k = 0; k < NPL; k++) {
+                    const int a = lane + k * LANES;
+                    pv[k] = a < OTH_NUM_ACTIONS ? pr[a] : 0.0f;
+                }
+                nn_value = P.values[slot];
             }
-            nn_value = P.values[slot];
         }
         load_counters();
         load_hot_head();
@@ -1006,6 +1034,34 @@ struct Ctx {
             // (2) no second round trip: the pending leaf's board / legal set / meta word and the
             //     path came with the hot record (only paths deeper than 8 need more of it)
             load_path_rest(c.path_len);
+            if constexpr (FUSED) {
+                // softmax over the 65 logits: max, exp, sum (lanes combined in a fixed order), divide
+                float mx = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < NPL; k++) mx = fmaxf(mx, pv[k]);
+                mx = redux_max_f32(mx, gmask);
+                float sum = 0.0f;
+#pragma unroll
+                for (int k = 0; k < NPL; k++) {
+                    const int a = lane + k * LANES;
+                    pv[k] = a < OTH_NUM_ACTIONS ? expf(pv[k] - mx) : 0.0f;
+                    sum = __fadd_rn(sum, pv[k]);
+                }
+#pragma unroll
+                for (int o = LANES / 2; o; o >>= 1) sum = __fadd_rn(sum, __shfl_down_sync(gmask, sum, o, LANES));
+                sum = gshfl(sum, 0);
+#pragma unroll
+                for (int k = 0; k < NPL; k++) pv[k] = __fdiv_rn(pv[k], sum);
+                nn_value = tanhf(nn_value);
+                if (P.priors_out) {
+#pragma unroll
+                    for (int k = 0; k < NPL; k++) {
+                        const int a = lane + k * LANES;
+                        if (a < OTH_NUM_ACTIONS) P.priors_out[(size_t)slot * OTH_NUM_ACTIONS + a] = pv[k];
+                    }
+                    if (lane == 0) P.values_out[slot] = nn_value;
+                }
+            }
             Node lf;
             lf.moves = S.hot.leaf_moves;
             lf.meta = S.hot.leaf_meta;
@@ -1112,6 +1168,20 @@ __global__ void __launch_bounds__(kBlock, 8) k_mcts_step(const Params P)
     for (int s = (blockIdx.x * kBlock + threadIdx.x) / LANES; s < P.cfg.n_slots; s += groups) {
         ctx.slot = s;
         ctx.template run_slot<false, false>();
+    }
+}
+
+// The hot kernel with the network's softmax / tanh fused in (oth_mcts_step_fused).
+template <int LANES>
+__global__ void __launch_bounds__(kBlock, 8) k_mcts_step_fused(const Params P)
+{
+    __shared__ Scratch scratch[kBlock / LANES];
+    cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
+    Ctx<LANES> ctx(tile, P, scratch[threadIdx.x / LANES]);
+    const int groups = (gridDim.x * kBlock) / LANES;
+    for (int s = (blockIdx.x * kBlock + threadIdx.x) / LANES; s < P.cfg.n_slots; s += groups) {
+        ctx.slot = s;
+        ctx.template run_slot<false, false, true>();
     }
 }
 
@@ -1372,6 +1442,11 @@ int make_params(const oth_mcts_config* cfg, const oth_mcts_buffers* b, Params* p
     p->move_flags = (uint8_t*)b->buf[OTH_BUF_MOVE_FLAGS];
     p->priors = nullptr;
     p->values = nullptr;
+    p->logits = nullptr;
+    p->vpre = nullptr;
+    p->logits_stride = p->vpre_stride = p->raw_bf16 = 0;
+    p->priors_out = nullptr;
+    p->values_out = nullptr;
     p->nn_input = nullptr;
     p->c_puct_f32 = (float)cfg->c_puct;
     return OTH_OK;
@@ -1486,6 +1561,33 @@ extern "C" int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers*
             const int blocks = (warps + kBlock / 32 - 1) / (kBlock / 32);
             k_mcts_move<<<blocks < sm_count() * 4 ? blocks : sm_count() * 4, kBlock, 0, (cudaStream_t)stream>>>(p);
         }
+    }
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int oth_mcts_step_fused(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const void* logits, int64_t logits_stride,
+                                   const void* value_preact, int64_t value_stride, int32_t is_bf16, float* priors_out, float* values_out,
+                                   float* nn_input, void* stream)
+{
+    Params p;
+    const int rc = make_params(cfg, b, &p);
+    if (rc != OTH_OK) return rc;
+    if (cfg->eval_kind != OTH_EVAL_EXTERNAL || !logits || !value_preact || !nn_input || logits_stride < OTH_NUM_ACTIONS || value_stride < 1 ||
+        (priors_out == nullptr) != (values_out == nullptr))
+        return OTH_E_ARG;
+    p.logits = logits;
+    p.vpre = value_preact;
+    p.logits_stride = (int)logits_stride;
+    p.vpre_stride = (int)value_stride;
+    p.raw_bf16 = is_bf16 ? 1 : 0;
+    p.priors_out = priors_out;
+    p.values_out = values_out;
+    p.nn_input = nn_input;
+    LAUNCH_LANES(k_mcts_step_fused, mcts_grid(cfg), stream, p);
+    if (cfg->self_play) {
+        const int warps = (cfg->n_slots + 31) / 32;
+        const int blocks = (warps + kBlock / 32 - 1) / (kBlock / 32);
+        k_mcts_move<<<blocks < sm_count() * 4 ? blocks : sm_count() * 4, kBlock, 0, (cudaStream_t)stream>>>(p);
     }
     return cuda_status(cudaGetLastError());
 }

@@ -139,6 +139,17 @@ class MctsEngine:
                    self._stream())
         self.launches += 1
 
+    def step_fused(self, logits, value_preact, record=False):
+        """``step`` with the network's softmax / tanh applied in-kernel: ``logits`` [n_slots, >=65] and
+        ``value_preact`` [n_slots, >=1] are (possibly strided) float32 or bfloat16 views of the head outputs.
+        ``record=True`` writes the priors / values the kernel used to ``self.priors`` / ``self.values``."""
+        assert logits.dtype == value_preact.dtype and logits.dtype in (torch.float32, torch.bfloat16)
+        assert logits.stride(1) == 1 and logits.size(0) == self.n_slots and value_preact.size(0) == self.n_slots
+        self._call(self.L.oth_mcts_step_fused, logits.data_ptr(), logits.stride(0), value_preact.data_ptr(), value_preact.stride(0),
+                   1 if logits.dtype == torch.bfloat16 else 0, self.priors.data_ptr() if record else None,
+                   self.values.data_ptr() if record else None, self.nn_input.data_ptr(), self._stream())
+        self.launches += 1
+
     def advance(self, actions):
         self._call(self.L.oth_mcts_advance, actions.data_ptr(), self._stream())
 
@@ -206,13 +217,21 @@ class BatchedPolicy:
         if dtype != torch.float32:
             self.policy = self.policy.to(memory_format=torch.channels_last)
 
+    @property
+    def has_raw(self):
+        return bool(getattr(self.policy, "supports_raw", False))
+
+    @torch.no_grad()
+    def raw(self, x):
+        """(logits [B,65], value pre-activation [B,1]) views of the twin's head GEMM outputs."""
+        return self.policy(x, raw=True)
+
     @torch.no_grad()
     def __call__(self, x, priors_out, values_out):
-        if getattr(self.policy, "raw_outputs", None) is not None:
+        if self.has_raw:
             # network twin: logits / value pre-activation straight from the head GEMMs; one softmax kernel
             # (cast fused) and one cast + one tanh for the values
-            self.policy.raw_outputs = True
-            logits, v = self.policy(x)
+            logits, v = self.policy(x, raw=True)
             torch.softmax(logits, dim=-1, dtype=torch.float32, out=priors_out)
             values_out.copy_(v.reshape(-1))
             values_out.tanh_()
@@ -230,15 +249,21 @@ class SelfPlayRunner:
     """Batched replacement of ``Trainer.collect_self_play_games`` (train.py:199-225):
     plays ``n_slots`` concurrent games with one network evaluation per simulation per game."""
 
-    def __init__(self, engine, evaluator=None, use_graph=True):
+    def __init__(self, engine, evaluator=None, use_graph=True, fused=True):
         self.e = engine
         self.evaluator = evaluator
         self.external = engine.cfg.eval_kind == _lib.EVAL_EXTERNAL
         assert not self.external or evaluator is not None
         self.use_graph = use_graph
         self.graph = None
+        # network twins hand the kernel raw logits: softmax / tanh are fused into oth_mcts_step_fused
+        self.fused = fused and self.external and getattr(evaluator, "raw", None) is not None and evaluator.has_raw
 
     def _iteration(self):
+        if self.external and self.fused:
+            logits, v = self.evaluator.raw(self.e.nn_input)
+            self.e.step_fused(logits, v)
+            return
         if self.external:
             self.evaluator(self.e.nn_input, self.e.priors, self.e.values)
         self.e.step()

@@ -286,10 +286,16 @@ def run_b200(a):
     torch.cuda.synchronize(dev)
     c0 = eng.counters()
     for i in range(iters):
-        ev(eng.nn_input, eng.priors, eng.values)
-        ev0[i].record()
-        eng.step()
-        ev1[i].record()
+        if run.fused:  # same launch as in the timed region: softmax / tanh fused into the step kernel
+            lg, vp = ev.raw(eng.nn_input)
+            ev0[i].record()
+            eng.step_fused(lg, vp)
+            ev1[i].record()
+        else:
+            ev(eng.nn_input, eng.priors, eng.values)
+            ev0[i].record()
+            eng.step()
+            ev1[i].record()
     torch.cuda.synchronize(dev)
     c1 = eng.counters()
     dk = {k: c1[k] - c0[k] for k in c1}
@@ -337,7 +343,7 @@ def run_b200(a):
             # k_bias_add_relu_bf16 per residual block of the network twin
             "gpu_launches": a.steps * iters * (3 + (5 if kind == "big" else 1)),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": f"k_mcts_step<{a.lanes}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": f"k_mcts_step{'_fused' if run.fused else ''}<{a.lanes}> (+ k_mcts_move)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "launch_ms_avg": k_avg, "launch_ms_median": kms[len(kms) // 2], "launch_ms_max": kms[-1],
                          "launch_ms_p90": kms[int(len(kms) * 0.9)],

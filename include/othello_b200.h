@@ -271,6 +271,15 @@ int oth_mcts_begin_search(const oth_mcts_config* cfg, const oth_mcts_buffers* b,
 int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const float* priors, const float* values,
                   float* nn_input, void* stream);
 
+/* oth_mcts_step with the network's tail fused in: `logits` [n_slots] rows of >= 65 raw policy logits
+ * (row stride in elements) and `value_preact` [n_slots] pre-tanh values (stride in elements), both
+ * float32 (is_bf16 = 0) or bfloat16 (1) -- typically views into the head GEMM outputs.  The kernel
+ * applies softmax over the 65 logits (Models.py:24-25) and tanh itself.  priors_out / values_out
+ * (both or neither): float32 [n_slots][65] / [n_slots] receive what it applied, for record & replay. */
+int oth_mcts_step_fused(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const void* logits, int64_t logits_stride,
+                        const void* value_preact, int64_t value_stride, int32_t is_bf16, float* priors_out, float* values_out,
+                        float* nn_input, void* stream);
+
 /* Refresh OTH_BUF_COUNTERS: sums the per-slot event counters and derives the gauges (WAITING /
  * ACTIVE / ERRORS / MAX_TOP) from the control blocks.  Kept out of the hot kernel; hosts call
  * it when they want totals or need to know whether to stop. */

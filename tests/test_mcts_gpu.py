@@ -304,3 +304,47 @@ def test_many_simulations_deep_tree_matches_oracle():
         assert len(traj) == len(ref["values"])
         assert np.array_equal(np.stack([t[1] for t in traj]), ref["pis"]), g
         assert np.array_equal(np.array([t[2] for t in traj]), ref["values"]), g
+
+
+def test_fused_softmax_path_record_and_replay():
+    """oth_mcts_step_fused: the kernel applies softmax / tanh to raw (bf16, strided) head outputs itself; the
+    priors and values it used are written back, recorded and replayed through the oracle."""
+    import torch
+    import oracle as O
+    from alphazero_othello_b200 import _lib
+    from alphazero_othello_b200.engine import MctsEngine, split_games
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(64, 96), torch.nn.Tanh(), torch.nn.Linear(96, 128)).cuda()
+    args = {"c_puct": 2.0, "num_simulations": 20, "dirichlet_alpha": 1.0, "dirichlet_epsilon": 0.3,
+            "mcts_temperature": 1.0, "num_exploratory_moves": 12, "lambda": 0.98}
+    n = 12
+    e = MctsEngine(n, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=1, seed=6)
+    table = O.EvalTable(1 << 18)
+    e.reset()
+    e.step()
+    w = (1 << (63 - np.arange(64, dtype=np.uint64)))
+    for it in range(40000):
+        ph = e.ctl()["phase"]
+        if not ((ph == _lib.PH_RUN) | (ph == _lib.PH_WAIT_EVAL)).any():
+            break
+        x = e.nn_input.view(n, 64).cpu().numpy()
+        with torch.no_grad():
+            y = (3.0 * net(e.nn_input.view(n, 64))).to(torch.bfloat16)  # [n,128]: logits in cols 0..64, value pre-activation col 100
+        e.step_fused(y[:, :65], y[:, 100:101], record=True)
+        pr, va = e.priors.cpu().numpy(), e.values.cpu().numpy()
+        ref_p = torch.softmax(y[:, :65].float(), -1).cpu().numpy()
+        for s in np.nonzero(ph == _lib.PH_WAIT_EVAL)[0]:
+            assert np.abs(pr[s] - ref_p[s]).max() < 1e-6 and abs(va[s] - np.tanh(float(y[s, 100]))) < 1e-6
+            own = int((w * (x[s] == 1)).sum()); opp = int((w * (x[s] == -1)).sum())
+            assert table.put(own, opp, pr[s], va[s]) in (0, 1)
+    e.raise_on_error()
+    noise = e.noise.cpu().numpy(); um = e.u_move.cpu().numpy(); ut = e.u_tie.cpu().numpy()
+    games = split_games(e.drain())
+    assert len(games) == n
+    for g in range(n):
+        ref = O.self_play(args, O.Evaluator(table=table), noise[g], um[g], ut[g])
+        traj = games[g]
+        assert len(traj) == len(ref["values"])
+        assert np.array_equal(np.stack([t[1] for t in traj]), ref["pis"])
+        assert np.array_equal(np.array([t[2] for t in traj]), ref["values"])
+    assert table.misses == 0
