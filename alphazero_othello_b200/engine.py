@@ -15,8 +15,9 @@ from . import _lib
 
 def default_node_cap(num_simulations):
     """Arena size per slot: kept subtree + one expansion (<= 33 children) per simulation,
-    with headroom; measured maxima are ~6.3k slots at 400 simulations."""
-    return int(max(2048, 40 * num_simulations + 1024))
+    with headroom; measured high-water marks: 13.6k of 20.2k nodes at 400 simulations (16 384 complete games),
+    5.5k of 10.6k at 200."""
+    return int(max(2048, 48 * num_simulations + 1024))
 
 
 class MctsEngine:
