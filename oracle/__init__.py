@@ -62,6 +62,7 @@ def lib():
         L.orc_mcts_root_stats.argtypes = [vp, vp, vp, vp, vp, vp]
         L.orc_mcts_counters.argtypes = [vp, vp]
         L.orc_mcts_policy.argtypes = [vp, f64, f64, vp]
+        L.orc_philox4x32_10.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, vp]
         L.orc_mcts_set_rollout.argtypes = [vp, C.c_uint64, C.c_uint64]
         L.orc_mcts_set_ply.argtypes = [vp, i32]
         L.orc_mcts_make_move.argtypes = [vp, i32]
@@ -295,6 +296,13 @@ def self_play(args, evaluator, noise, u_move, u_tie=None, max_plies=128):
                 root_values=rvals[:n], actions=actions[:n], counts=counts[:n],
                 counters=dict(evals=int(counters[0]), sims=int(counters[1]), nodes=int(counters[2]),
                               max_depth=int(counters[3]), max_children=int(counters[4])))
+
+
+def philox(seed, ctr_lo, h0, h1):
+    """Philox4x32-10 block (four uint32) for key ``seed`` and counter (ctr_lo, h0, h1)."""
+    out = np.zeros(4, np.uint32)
+    lib().orc_philox4x32_10(int(seed), int(ctr_lo), int(h0), int(h1), _p(out))
+    return out
 
 
 def random_playout(seed, max_plies=128):

@@ -101,7 +101,7 @@ def test_rollout_traces_replay_through_oracle():
     import oracle as O
     from alphazero_othello_b200.envs.othello import BatchedOthello
     env = BatchedOthello()
-    n, n_trace = 8192, 192
+    n, n_trace = 8192, 1024
     r = env.rollout(n, seed=7, n_trace=n_trace)
     torch.cuda.synchronize()
     acts = r["trace_actions"].cpu().numpy()
@@ -225,3 +225,25 @@ def test_device_symmetry_batch_vs_oracle():
     r1, q1 = env.random_symmetry(torch.from_numpy(S).cuda(), torch.from_numpy(P).cuda())
     assert torch.equal(r1.abs().sum((1, 2, 3)), torch.from_numpy(np.abs(S).sum((1, 2)).astype(np.float32)).cuda())
     assert torch.allclose(q1.sum(1), torch.from_numpy(P.sum(1)).cuda(), atol=1e-4)
+
+
+def test_rollout_rng_contract_philox_keyed_by_game_and_ply():
+    """include/othello_b200.h: game g draws from Philox4x32-10 keyed (seed; game_id_base+g, ply>>2), word ply&3,
+    and plays the floor(u32 * n_legal / 2^32)-th legal square in ascending order.  Restated on the host."""
+    import torch
+    import oracle as O
+    from alphazero_othello_b200.envs.othello import BatchedOthello
+    env = BatchedOthello()
+    seed, base = 123456789, 777
+    r = env.rollout(64, seed=seed, game_id_base=base, n_trace=64)
+    torch.cuda.synchronize()
+    acts = r["trace_actions"].cpu().numpy(); moves = r["trace_moves"].cpu().numpy().view(np.uint64); plies = r["plies"].cpu().numpy()
+    for g in range(64):
+        for t in range(plies[g]):
+            m = int(moves[g, t])
+            if m == 0:
+                assert acts[g, t] == 64
+                continue
+            legal = [i for i in range(64) if (m >> i) & 1]
+            word = int(O.philox(seed, base + g, t >> 2, 0)[t & 3])
+            assert acts[g, t] == legal[(word * len(legal)) >> 32], (g, t)

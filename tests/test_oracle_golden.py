@@ -137,3 +137,11 @@ def test_choice_model(golden):
         ref = rs.choice(65, p=p)
         sh = np.random.RandomState(); sh.set_state(st)
         assert O.choice(p, sh.random_sample()) == ref
+
+
+def test_philox_known_answer():
+    # Random123 known-answer vector for Philox4x32-10: counter = key = 0
+    assert [hex(int(x)) for x in O.philox(0, 0, 0, 0)] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    # all-ones counter and key (Random123 kat_vectors)
+    full = (1 << 64) - 1
+    assert [hex(int(x)) for x in O.philox(full, full, 0xffffffff, 0xffffffff)] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
