@@ -103,8 +103,12 @@ __global__ void __launch_bounds__(256) k_rollout(uint64_t seed, uint64_t base, i
         int plies = 0;
         u64 m = legal_moves(own, opp);
         Philox4 r = {0, 0, 0, 0};
+        int block = -1;  // Philox block (ply >> 2) currently held in r; a forced pass can skip a block boundary
         while (plies < OTH_MAX_PLIES) {
-            if ((plies & 3) == 0) r = philox4x32_10(seed, gid, (uint32_t)(plies >> 2), 0u);
+            if ((plies >> 2) != block) {
+                block = plies >> 2;
+                r = philox4x32_10(seed, gid, (uint32_t)block, 0u);
+            }
             const int w = plies & 3;
             const uint32_t rnd = w == 0 ? r.x : (w == 1 ? r.y : (w == 2 ? r.z : r.w));
             const int nm = __popcll(m);
