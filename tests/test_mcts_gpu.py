@@ -348,3 +348,21 @@ def test_fused_softmax_path_record_and_replay():
         assert np.array_equal(np.stack([t[1] for t in traj]), ref["pis"])
         assert np.array_equal(np.array([t[2] for t in traj]), ref["values"])
     assert table.misses == 0
+
+
+def test_move_uniforms_follow_the_documented_philox_streams():
+    """u_move / u_tie of ply t in game id G = u01_53(Philox4x32-10(seed; G, t, purpose 1 / 2)) (csrc/philox.cuh)."""
+    import oracle as O
+    args = {"c_puct": 2.0, "num_simulations": 8, "dirichlet_alpha": 1.0, "dirichlet_epsilon": 0.3,
+            "mcts_temperature": 1.0, "num_exploratory_moves": 5, "lambda": 0.98}
+    e = _selfplay_engine(args, 8, 5, False, 3, seed=2024, game_id_base=40)
+    _run_to_done(e)
+    um, ut = e.u_move.cpu().numpy(), e.u_tie.cpu().numpy()
+    out = e.drain()
+    for gid, first, n, _w in out["games"].numpy():
+        slot = int(gid) - 40
+        for t in range(int(n)):
+            for purpose, got in ((1, um[slot, t]), (2, ut[slot, t])):
+                w = O.philox(2024, int(gid), t, purpose)
+                exp = ((int(w[0]) >> 5) * 67108864.0 + (int(w[1]) >> 6)) / 9007199254740992.0
+                assert got == exp, (gid, t, purpose)
