@@ -366,3 +366,23 @@ def test_move_uniforms_follow_the_documented_philox_streams():
                 w = O.philox(2024, int(gid), t, purpose)
                 exp = ((int(w[0]) >> 5) * 67108864.0 + (int(w[1]) >> 6)) / 9007199254740992.0
                 assert got == exp, (gid, t, purpose)
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.3, 0.03])
+def test_dirichlet_noise_is_a_dirichlet_draw(alpha):
+    """Root noise is drawn in-kernel (Marsaglia-Tsang gammas from Philox, normalised): check the moments of
+    Dirichlet(alpha * 1_65) over 16 384 independent slots -- np.random.dirichlet([alpha]*65), MCTS_model.py:341."""
+    args = {"c_puct": 2.0, "num_simulations": 4, "dirichlet_alpha": alpha, "dirichlet_epsilon": 0.25}
+    e = _selfplay_engine(args, 8, 16384, False, 0, seed=77)
+    e.reset()
+    nz = e.noise.cpu().numpy()
+    assert nz.shape == (16384, 65) and (nz >= 0).all() and np.allclose(nz.sum(1), 1.0, atol=1e-12)
+    a0 = 65 * alpha
+    var = alpha * (a0 - alpha) / (a0 * a0 * (a0 + 1))
+    assert abs(nz.mean() - 1 / 65) < 1e-12 + 1e-9  # rows sum to one exactly
+    assert np.abs(nz.mean(0) - 1 / 65).max() < 6 * np.sqrt(var / 16384)
+    assert abs(nz.var(0).mean() / var - 1) < 0.03
+    # independent across slots and reproducible from (seed, game id)
+    e2 = _selfplay_engine(args, 32, 64, False, 0, seed=77)
+    e2.reset()
+    assert np.array_equal(e2.noise.cpu().numpy(), nz[:64]) and not np.array_equal(nz[0], nz[1])
