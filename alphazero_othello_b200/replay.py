@@ -63,3 +63,47 @@ def pack_states(states):
     own = ((s == 1) * w).sum(1, dtype=np.uint64)
     opp = ((s == -1) * w).sum(1, dtype=np.uint64)
     return torch.from_numpy(np.stack([own, opp], 1).view(np.int64))
+
+
+class ReplayBuffer:
+    """GPU-resident replay buffer with the semantics of the reference's ``deque(maxlen=...)`` of
+    ``(state, pi, value, model_version)`` tuples (train.py:77-82, 136-140): ``extend`` appends the
+    drained self-play output tagged with the current model version, the oldest tuples fall out when
+    the capacity is exceeded, ``aggregate`` is ``_aggregate_duplicates`` over the buffer in
+    chronological order (oldest first, which fixes the bucket order)."""
+
+    def __init__(self, capacity, device="cuda:0"):
+        self.capacity = int(capacity)
+        self.device = torch.device(device)
+        self.boards = torch.zeros((self.capacity, 2), dtype=torch.int64, device=self.device)
+        self.pis = torch.zeros((self.capacity, 65), dtype=torch.float32, device=self.device)
+        self.values = torch.zeros(self.capacity, dtype=torch.float64, device=self.device)
+        self.versions = torch.zeros(self.capacity, dtype=torch.int32, device=self.device)
+        self.head = 0  # next write position
+        self.size = 0
+
+    def __len__(self):
+        return self.size
+
+    def extend(self, drained, version):
+        """``drained``: output of ``MctsEngine.drain`` (or any dict with boards / pis / values)."""
+        b = drained["boards"].to(self.device, torch.int64)
+        p = drained["pis"].to(self.device, torch.float32)
+        v = drained["values"].to(self.device, torch.float64)
+        n = int(v.numel())
+        if n > self.capacity:  # only the newest `capacity` tuples can survive
+            b, p, v, n = b[-self.capacity:], p[-self.capacity:], v[-self.capacity:], self.capacity
+        idx = (self.head + torch.arange(n, device=self.device)) % self.capacity
+        self.boards[idx], self.pis[idx], self.values[idx] = b, p, v
+        self.versions[idx] = int(version)
+        self.head = (self.head + n) % self.capacity
+        self.size = min(self.capacity, self.size + n)
+
+    def chronological(self):
+        """(boards, pis, values, versions) oldest first."""
+        start = (self.head - self.size) % self.capacity
+        idx = (start + torch.arange(self.size, device=self.device)) % self.capacity
+        return self.boards[idx], self.pis[idx], self.values[idx], self.versions[idx]
+
+    def aggregate(self):
+        return aggregate_duplicates(*self.chronological(), device=self.device)

@@ -71,3 +71,28 @@ def test_gpu_empty_and_singleton():
     p = pi[0].numpy().copy()
     p = (p / np.float32(1)) ; p /= p.sum() + 1e-12
     assert np.array_equal(one["pis"].cpu().numpy()[0], p.astype(np.float32))
+
+
+@pytest.mark.gpu
+def test_replay_buffer_matches_deque_semantics():
+    """extend + maxlen eviction + aggregate == the reference's deque + _aggregate_duplicates (oracle restatement)."""
+    import collections
+    import torch
+    from alphazero_othello_b200 import replay
+    rs = np.random.RandomState(9)
+    uniq = rs.randint(-1, 2, size=(40, 8, 8)).astype(np.int8)
+    cap = 500
+    buf = replay.ReplayBuffer(cap)
+    ref = collections.deque(maxlen=cap)
+    for it in range(7):
+        n = int(rs.randint(50, 200))
+        states = uniq[rs.randint(0, 40, n)]
+        pis = rs.rand(n, 65).astype(np.float32)
+        values = rs.uniform(-1, 1, n)
+        buf.extend(dict(boards=replay.pack_states(states), pis=torch.from_numpy(pis), values=torch.from_numpy(values)), version=it // 2)
+        ref.extend((s, p.copy(), float(v), it // 2) for s, p, v in zip(states, pis, values))
+    assert len(buf) == len(ref) == cap
+    exp = OR.aggregate_duplicates(list(ref))
+    st, po, va = replay.to_training_arrays(buf.aggregate())
+    assert np.array_equal(st.cpu().numpy().astype(np.int8), np.stack(exp[0]))
+    assert np.array_equal(po.cpu().numpy(), np.stack(exp[1])) and np.array_equal(va.cpu().numpy().ravel(), np.array(exp[2], np.float32))
