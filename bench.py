@@ -401,6 +401,46 @@ def aux_env(dev):
                                               "k_rollout's shift/logic mix can only use the ALU pipe)", **ncu}}
 
 
+def aux_env_step_api(dev):
+    """Stepwise env API on packed boards (oth_legal_moves / oth_step): HBM-bound, 24 / 42 bytes per position."""
+    import torch
+    from alphazero_othello_b200.envs.othello import BatchedOthello
+    env = BatchedOthello(dev)
+    n = 1 << 24
+    own, opp = env.initial(n)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0)
+    for ply in range(16):  # mid-game positions: 16 plies, each the r-th lowest legal square (r random per game)
+        lm = env.legal_moves(own, opp)
+        r = torch.randint(0, 4, (n,), device=dev, generator=gen)
+        pick = lm
+        for _ in range(3):  # clear up to r lowest bits, keeping at least one
+            nxt = pick & (pick - 1)
+            pick = torch.where((r > 0) & (nxt != 0), nxt, pick)
+            r = r - 1
+        bit = pick & (-pick)
+        act = torch.where(lm == 0, torch.full_like(bit, 64), (torch.log2(bit.double().abs()) + 0.5).long() % 64)
+        act = torch.where((bit < 0) & (lm != 0), torch.full_like(act, 63), act).to(torch.uint8)
+        own, opp, _, fl = env.step(own, opp, act)
+        assert int((fl & 1).sum()) == 0
+    peak, _ = measured_peaks()
+    out = {}
+    for name, fn, nbytes in (("legal_moves", lambda: env.legal_moves(own, opp), 24), ("step", lambda: env.step(own, opp, act), 42)):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 5
+        out[name] = {"positions_per_s": n / (ms * 1e-3), "ms": ms, "bytes_per_position": nbytes,
+                     "hbm_gbs": n * nbytes / (ms * 1e-3) / 1e9, "hbm_frac": n * nbytes / (ms * 1e-3) / 1e9 / peak}
+    out["workload"] = f"{n} mid-game positions (16 plies in), packed boards resident in HBM (> L2), includes torch output allocation"
+    return out
+
+
 def aux_search_only(dev, G, sims, lanes):
     """Search-only variant: the same kernel with the device hash-stub evaluator, so a
     launch runs whole simulations back to back without the network in between."""
@@ -478,6 +518,7 @@ def main():
         if world == 1 and not a.no_aux:
             out["aux"] = aux_env(dev)
             out["aux"]["search_only"] = aux_search_only(dev, out["config"]["games_per_gpu"], sims, a.lanes)
+            out["aux"]["env_step_api"] = aux_env_step_api(dev)
         if world == 1 and not a.no_cpu_baseline:
             import oracle
             oracle.build()
