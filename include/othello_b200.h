@@ -238,6 +238,10 @@ typedef struct oth_mcts_buffers {
     void* buf[OTH_BUF_COUNT];
 } oth_mcts_buffers;
 
+/* Sizes (bytes) of the OTH_BUF_* buffers for a configuration.  The caller allocates them in device
+ * memory (16-byte aligned; cudaMalloc / torch give far more) and ZERO-FILLS them once before the first
+ * oth_mcts_reset / oth_mcts_set_roots: a zeroed control block means "slot has no tree yet" and is
+ * skipped by every kernel. */
 int oth_mcts_buffer_bytes(const oth_mcts_config* cfg, int64_t* out_bytes /* [OTH_BUF_COUNT] */);
 
 /* Start every slot on a fresh game from the initial position (one_self_play's
