@@ -107,3 +107,50 @@ class ReplayBuffer:
 
     def aggregate(self):
         return aggregate_duplicates(*self.chronological(), device=self.device)
+
+    # ------------------------------------------------------- on-disk format
+    def to_reference_tuples(self):
+        """The buffer as the reference keeps it in memory and on disk: ``deque(maxlen=capacity)`` of
+        ``(state int8[8,8] canonical, policy_target float32[65], value_target float, version int)``
+        (train.py:77-82, README.md:85-88), oldest first."""
+        from collections import deque
+        b, p, v, ver = self.chronological()
+        n = int(v.numel())
+        states = torch.empty((n, 8, 8), dtype=torch.int8, device=self.device)
+        if n:
+            _lib.require_device()
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().oth_unpack_canonical(b.contiguous().data_ptr(), states.data_ptr(), n,
+                                                           C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        states, p, v, ver = states.cpu().numpy(), p.cpu().numpy(), v.cpu().numpy(), ver.cpu().numpy()
+        return deque(((states[i], p[i], float(v[i]), int(ver[i])) for i in range(n)), maxlen=self.capacity)
+
+    def save(self, path):
+        """``Trainer._save_replay_buffer`` (train.py:104-111): pickle of the whole deque, atomic replace."""
+        import os
+        import pickle
+        tmp = path + ".tmp"
+        with open(tmp, "wb") as f:
+            pickle.dump(self.to_reference_tuples(), f, protocol=pickle.HIGHEST_PROTOCOL)
+        os.replace(tmp, path)
+
+    def load(self, path):
+        """``Trainer._load_replay_buffer`` (train.py:113-134): replaces the contents with the pickled
+        tuples (keeping this buffer's capacity: the newest survive) and returns the latest model
+        version found (0 for an empty file or 3-tuples).  Accepts replay files written by the reference."""
+        import pickle
+        with open(path, "rb") as f:
+            loaded = list(pickle.load(f))
+        self.head = self.size = 0
+        if not loaded:
+            return 0
+        loaded = loaded[-self.capacity:]
+        has_ver = [isinstance(t, (tuple, list)) and len(t) >= 4 for t in loaded]
+        vers = np.array([int(t[3]) if h else 0 for t, h in zip(loaded, has_ver)], np.int32)
+        n = len(loaded)
+        self.boards[:n] = pack_states(np.stack([np.asarray(t[0]).reshape(8, 8) for t in loaded])).to(self.device)
+        self.pis[:n] = torch.from_numpy(np.stack([np.asarray(t[1], np.float32) for t in loaded])).to(self.device)
+        self.values[:n] = torch.tensor([float(t[2]) for t in loaded], dtype=torch.float64, device=self.device)
+        self.versions[:n] = torch.from_numpy(vers).to(self.device)
+        self.head, self.size = n % self.capacity, n
+        return int(max((int(t[3]) for t, h in zip(loaded, has_ver) if h), default=0))

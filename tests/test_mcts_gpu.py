@@ -386,3 +386,57 @@ def test_dirichlet_noise_is_a_dirichlet_draw(alpha):
     e2 = _selfplay_engine(args, 32, 64, False, 0, seed=77)
     e2.reset()
     assert np.array_equal(e2.noise.cpu().numpy(), nz[:64]) and not np.array_equal(nz[0], nz[1])
+
+
+def test_full_size_c4_whole_games_invariants_and_sampled_oracle_replay():
+    """BASELINE configs[3] geometry -- 16 384 concurrent games, 400 simulations per move, the training
+    hyper-parameters -- played to the end with the device stub evaluator (the network is not part of
+    this check).  Size-independent properties over ALL ~10^6 positions, and 24 games sampled across the
+    slot range replayed through the oracle from the recorded draws: every tuple bit for bit."""
+    import torch
+    import oracle as O
+    from alphazero_othello_b200.envs.othello import BatchedOthello
+    args = {"c_puct": 2.0, "num_simulations": 400, "dirichlet_alpha": 1.0, "dirichlet_epsilon": 0.3,
+            "mcts_temperature": 1.0, "num_exploratory_moves": 35, "lambda": 0.98}
+    n = 16384
+    e = _selfplay_engine(args, 8, n, False, 7, seed=2024, max_inline_sims=16, out_pos_cap=n * 72, out_game_cap=n + 16)
+    _run_to_done(e, max_launches=40000)
+    c = e.counters()
+    assert c["games"] == n and c["errors"] == 0
+    noise = e.noise.cpu().numpy(); um = e.u_move.cpu().numpy(); ut = e.u_tie.cpu().numpy()
+    out = e.drain(to_host=False)
+    games = out["games"].cpu().numpy()
+    assert sorted(games[:, 0].tolist()) == list(range(n))                 # every game id exactly once
+    npos = int(out["values"].numel())
+    assert npos == int(games[:, 2].sum()) == c["moves"]                   # one tuple per move
+    assert c["sims"] == 400 * c["moves"]                                  # num_simulations per search, every search
+    assert 4 <= games[:, 2].min() and games[:, 2].max() <= 128
+    # ranges of the descriptors tile the output ring without gaps or overlaps
+    order = np.argsort(games[:, 1])
+    assert games[order[0], 1] == 0 and np.array_equal(games[order, 1][1:], (games[order, 1] + games[order, 2])[:-1])
+    # policy targets: non-negative, sum to 1, zero outside the legal set of that position (env kernel as checker)
+    pis = out["pis"]
+    assert float(pis.min()) >= 0.0 and float((pis.sum(1) - 1).abs().max()) <= 1e-5
+    env = BatchedOthello("cuda:0")
+    own, opp = out["boards"][:, 0].contiguous(), out["boards"][:, 1].contiguous()
+    lm = env.legal_moves(own, opp)
+    bits = ((lm.unsqueeze(1) >> torch.arange(64, device=lm.device)) & 1).bool()
+    legal65 = torch.cat([bits, (lm == 0).unsqueeze(1)], 1)
+    assert not bool((pis > 0)[~legal65].any())
+    assert bool(((pis > 0) & legal65).any(1).all())
+    assert int((own & opp).count_nonzero()) == 0
+    # value targets: |G| <= 1, and the last position of a game carries z in {-1, 0, +1}
+    v = out["values"]
+    assert float(v.abs().max()) <= 1.0
+    last = torch.from_numpy(games[:, 1] + games[:, 2] - 1).to(v.device)
+    assert bool(torch.isin(v[last], torch.tensor([-1.0, 0.0, 1.0], dtype=v.dtype, device=v.device)).all())
+    # sampled games through the oracle (ids spread over the slot range)
+    states, pis_h, v_h = out["states"].cpu().numpy(), pis.cpu().numpy(), v.cpu().numpy()
+    desc = {int(r[0]): (int(r[1]), int(r[2])) for r in games}
+    for g in list(range(0, n, n // 20)) + [1, n // 2 + 3, n - 2, n - 1]:
+        ref = O.self_play(args, O.Evaluator(stub=O.STUB_H, salt=7), noise[g], um[g], ut[g])
+        first, T = desc[g]
+        assert T == len(ref["values"]), g
+        assert np.array_equal(states[first:first + T], ref["states"]), g
+        assert np.array_equal(pis_h[first:first + T], ref["pis"]), g
+        assert np.array_equal(v_h[first:first + T], ref["values"]), g

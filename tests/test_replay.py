@@ -96,3 +96,45 @@ def test_replay_buffer_matches_deque_semantics():
     st, po, va = replay.to_training_arrays(buf.aggregate())
     assert np.array_equal(st.cpu().numpy().astype(np.int8), np.stack(exp[0]))
     assert np.array_equal(po.cpu().numpy(), np.stack(exp[1])) and np.array_equal(va.cpu().numpy().ravel(), np.array(exp[2], np.float32))
+
+
+@pytest.mark.gpu
+def test_replay_buffer_pickle_round_trip_in_the_reference_format(tmp_path):
+    """save() writes what Trainer._save_replay_buffer writes (train.py:104-111): a pickled
+    deque(maxlen) of (int8[8,8], float32[65], float, int); load() reads such a file back
+    (train.py:113-134), returns the latest model version and honours this buffer's capacity."""
+    import collections
+    import pickle
+    import torch
+    from alphazero_othello_b200 import replay
+    rs = np.random.RandomState(3)
+    n = 300
+    states = rs.randint(-1, 2, size=(n, 8, 8)).astype(np.int8)
+    pis = rs.rand(n, 65).astype(np.float32)
+    values = rs.uniform(-1, 1, n)
+    buf = replay.ReplayBuffer(256)
+    buf.extend(dict(boards=replay.pack_states(states[:200]), pis=torch.from_numpy(pis[:200]), values=torch.from_numpy(values[:200])), 3)
+    buf.extend(dict(boards=replay.pack_states(states[200:]), pis=torch.from_numpy(pis[200:]), values=torch.from_numpy(values[200:])), 4)
+    path = str(tmp_path / "replay.pkl")
+    buf.save(path)
+    with open(path, "rb") as f:
+        dq = pickle.load(f)
+    assert isinstance(dq, collections.deque) and dq.maxlen == 256 and len(dq) == 256
+    for k, (s, p, v, ver) in enumerate(dq):  # the newest 256 of the 300, oldest first
+        i = n - 256 + k
+        assert s.dtype == np.int8 and s.shape == (8, 8) and np.array_equal(s, states[i])
+        assert p.dtype == np.float32 and np.array_equal(p, pis[i])
+        assert isinstance(v, float) and v == values[i] and isinstance(ver, int) and ver == (3 if i < 200 else 4)
+    # a file as the reference writes it (plain deque of tuples, one legacy 3-tuple) into a smaller buffer
+    ref = collections.deque(maxlen=500000)
+    ref.extend((states[i], pis[i], float(values[i]), 7 + i // 100) for i in range(n))
+    ref.append((states[0], pis[0], 0.5))
+    with open(path, "wb") as f:
+        pickle.dump(ref, f, protocol=pickle.HIGHEST_PROTOCOL)
+    small = replay.ReplayBuffer(100)
+    assert small.load(path) == 9 and len(small) == 100
+    back = list(small.to_reference_tuples())
+    assert all(np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] for a, b in zip(back, list(ref)[-100:]))
+    assert [t[3] for t in back] == [9] * 99 + [0]
+    small.extend(dict(boards=replay.pack_states(states[:5]), pis=torch.from_numpy(pis[:5]), values=torch.from_numpy(values[:5])), 10)
+    assert len(small) == 100 and [t[3] for t in small.to_reference_tuples()][-6:] == [0, 10, 10, 10, 10, 10]
