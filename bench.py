@@ -81,6 +81,28 @@ def cpu_port_rate(kind, sims, steps, warm, cores):
     return cores * sims * steps / total, 1e3 * total / steps, wall
 
 
+def _cpu_env_worker(job):
+    seed0, seconds = job
+    import oracle as O
+    O.random_playout(seed0)  # load the library
+    plies = games = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for k in range(64):
+            plies += O.random_playout(seed0 + games + k)[0]
+        games += 64
+    return plies, games, time.perf_counter() - t0
+
+
+def cpu_env_rate(cores, seconds=2.0):
+    """Config C1 on the host: the oracle's Game-API random playout (legal mask, pick, next state,
+    terminal test per ply on int8[8,8] boards) on every core for `seconds`."""
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_cpu_env_worker, [(1000003 * i, seconds) for i in range(cores)])
+    return sum(r[0] for r in res) / max(r[2] for r in res), sum(r[1] for r in res)
+
+
 # ---------------------------------------------------------------- utilities --
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -354,9 +376,70 @@ def run_b200(a):
             "search_counters_per_step": {k: d[k] / a.steps for k in ("sims", "evals", "terminal_sims", "moves", "games", "nodes", "copied", "levels", "children")},
         }
     if world > 1:
+        if not a.no_aux:
+            env_aux = aux_env_sharded(dev, rank, world)
+            if rank == 0:
+                out["aux"] = env_aux
         dist.barrier()
         dist.destroy_process_group()
     return out, dev
+
+
+def aux_selfplay_rate(dev, workload, steps=8, warm=3):
+    """Resident self-play throughput of another BASELINE config on the same GPU (same pipeline as the
+    headline: network twin + oth_mcts_step_fused replayed as a CUDA graph; a step = sims/move iterations)."""
+    import torch
+    from alphazero_othello_b200 import _lib
+    from alphazero_othello_b200.Models import fold_for_inference
+    from alphazero_othello_b200.engine import BatchedPolicy, MctsEngine, SelfPlayRunner
+    desc, kind, G, sims = WORKLOADS[workload]
+    args = dict(TRAIN_ARGS, num_simulations=sims)
+    eng = MctsEngine(G, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=-1, device=dev,
+                     out_pos_cap=G * 80, out_game_cap=G + 64)
+    run = SelfPlayRunner(eng, BatchedPolicy(fold_for_inference(make_net(kind).to(dev), torch.bfloat16), dev, torch.float32))
+    run.warm_start()
+    for _ in range(warm):
+        run.run_iterations(sims)
+    torch.cuda.synchronize(dev)
+    c0 = eng.counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run.run_iterations(sims)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    c1 = eng.counters()
+    eng.raise_on_error()
+    ms = e0.elapsed_time(e1)
+    return {"workload": f"{workload}: {desc}", "net": kind, "sims_per_s": (c1["sims"] - c0["sims"]) / (ms * 1e-3),
+            "positions_per_s": (c1["moves"] - c0["moves"]) / (ms * 1e-3), "steps": steps, "warmup": warm, "ms_per_step": ms / steps}
+
+
+def aux_env_sharded(dev, rank, world):
+    """Config C1 over all ranks: every rank rolls out its own 2^22 games (ids offset by rank); whole-job
+    plies / max-over-ranks device time.  No collective on the path -- the all-reduce only gathers the timing."""
+    import torch
+    import torch.distributed as dist
+    from alphazero_othello_b200.envs.othello import BatchedOthello
+    env = BatchedOthello(dev)
+    n = 1 << 22
+    best = None
+    for rep in range(4):
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = env.rollout(n, seed=rep, game_id_base=rank * n)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        p = torch.tensor([float(int(r["counters"][0]))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(p)
+        if rep and (best is None or float(t) < best[0]):
+            best = (float(t), float(p))
+    return {"workload": f"c1: Othello 8x8 random-policy rollouts, 2^22 games per GPU x {world} GPUs",
+            "env_steps_per_s": best[1] / (best[0] * 1e-3), "kernel_ms_max_over_ranks": best[0], "plies": best[1]}
 
 
 def aux_env(dev):
@@ -519,6 +602,13 @@ def main():
             out["aux"] = aux_env(dev)
             out["aux"]["search_only"] = aux_search_only(dev, out["config"]["games_per_gpu"], sims, a.lanes)
             out["aux"]["env_step_api"] = aux_env_step_api(dev)
+            other = "c3" if a.workload != "c3" else "c4"  # north_star: both architectures
+            out["aux"]["other_architecture"] = aux_selfplay_rate(dev, other)
+            import oracle
+            oracle.build()
+            rate, games = cpu_env_rate(cores)
+            out["aux"]["cpu_env_baseline"] = {"value": rate, "unit": "env steps/s", "cores": cores, "kind": "port",
+                                              "sample": f"{games} random playouts (oracle Game-API loop on int8[8,8] boards), {cores} processes x 2 s"}
         if world == 1 and not a.no_cpu_baseline:
             import oracle
             oracle.build()
