@@ -116,9 +116,12 @@ def _fold(conv, bn):
 
 
 class _FusedConv(nn.Module):
-    """3x3 / 1x1 convolution + bias + ReLU in one cuDNN call; with a residual, cuDNN's plain
-    convolution followed by one in-place ``relu(x + bias + residual)`` pass
-    (``oth_nn_bias_add_relu_bf16``), which is faster than cuDNN's fused add-ReLU engine here."""
+    """3x3 / 1x1 convolution + bias + ReLU in one cuDNN call; with a residual, one cuDNN graph
+    ``relu(bias(conv + residual))`` (``_cudnn_fused``, batches >= 256), else cuDNN's plain convolution
+    followed by one in-place ``relu(x + bias + residual)`` pass (``oth_nn_bias_add_relu_bf16``) -- both
+    faster than ``torch.cudnn_convolution_add_relu``, which lands on a legacy engine here."""
+
+    graph_fusion = True  # class-wide switch (tests / A-B measurements)
 
     def __init__(self, w, b, dtype):
         super().__init__()
@@ -132,6 +135,12 @@ class _FusedConv(nn.Module):
             return torch.cudnn_convolution_relu(x, self.w, self.b, (1, 1), p, (1, 1), 1)
         if x.dtype != torch.bfloat16:
             return torch.cudnn_convolution_add_relu(x, self.w, residual, 1.0, self.b, (1, 1), p, (1, 1), 1)
+        if self.graph_fusion and x.is_contiguous(memory_format=torch.channels_last) \
+                and residual.is_contiguous(memory_format=torch.channels_last):
+            from . import _cudnn_fused
+            y = _cudnn_fused.conv_res_bias_relu(x, self.w, self.b, residual)  # one cuDNN graph (large batches)
+            if y is not None:
+                return y
         y = F.conv2d(x, self.w, None, 1, self.pad)
         assert y.is_contiguous(memory_format=torch.channels_last) and residual.is_contiguous(memory_format=torch.channels_last)
         import ctypes as C

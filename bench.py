@@ -342,6 +342,8 @@ def run_b200(a):
         traffic = json.load(open(prof)).get("dram_bytes_per_launch")
     eng.drain(to_host=False)
 
+    from alphazero_othello_b200 import _cudnn_fused
+    fused_plans = _cudnn_fused.chosen_plans()
     out = None
     if rank == 0:
         out = {
@@ -353,6 +355,8 @@ def run_b200(a):
                        "iters_per_step": iters, "lanes": a.lanes, "cuda_graph": not a.no_graph,
                        "l2": f"tree arenas {eng.buf_bytes[0] + eng.buf_bytes[1] >> 20} MiB per GPU >> 126 MB L2 (inputs larger than L2)",
                        "sharding": "games by id, no collective on the search path",
+                       "network_twin": {"residual_conv": "one cuDNN graph relu(bias(conv+residual)) per block" if fused_plans
+                                        else "cuDNN conv + k_bias_add_relu_bf16", "cudnn_plans": fused_plans},
                        "roofline_timing": "CUDA events around every oth_mcts_step launch (k_mcts_step + k_mcts_move) in an un-graphed "
                                           "pass of iters_per_step iterations of the same pipeline right after the timed region "
                                           "(events cannot be recorded inside the replayed graph)"},
@@ -361,9 +365,9 @@ def run_b200(a):
                     "d2h_bytes_per_step": io["d2h"] // a.steps, "ms_per_step": ms2 / a.steps,
                     "includes": "weights H2D from pinned host (+NCCL broadcast if sharded), BN re-fold, "
                                 "D2H of policy targets/root values and finished games' replay tuples (+gather to rank 0)"},
-            # this repo's kernels per iteration: k_mcts_step, k_mcts_move, k_stem_im2col_bf16 and one
-            # k_bias_add_relu_bf16 per residual block of the network twin
-            "gpu_launches": a.steps * iters * (3 + (5 if kind == "big" else 1)),
+            # this repo's kernels per iteration: k_mcts_step, k_mcts_move, k_stem_im2col_bf16 and -- only when the
+            # residual convolutions do not run as one cuDNN graph -- one k_bias_add_relu_bf16 per residual block
+            "gpu_launches": a.steps * iters * (3 + (0 if fused_plans else (5 if kind == "big" else 1))),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": f"k_mcts_step{'_fused' if run.fused else ''}<{a.lanes}> (+ k_mcts_move)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

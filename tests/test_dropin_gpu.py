@@ -136,3 +136,34 @@ def test_mcts_class_rollout_mode_finds_forced_win():
     legal = np.nonzero(env.get_valid_moves(s, 1))[0]
     assert set(np.nonzero(probs)[0]) <= set(legal)
     assert m.root.visit_count == 301
+
+
+def test_residual_conv_as_one_cudnn_graph_matches_the_two_kernel_path():
+    """Network boundary: relu(conv(x) + residual + bias) as one cuDNN graph (autotuned plan, also when
+    replayed from a CUDA graph) against cuDNN conv + k_bias_add_relu_bf16 and against float32."""
+    import torch
+    from alphazero_othello_b200 import _cudnn_fused
+    from alphazero_othello_b200.Models import _FusedConv
+    torch.manual_seed(3)
+    B, C = 2048, 128
+    conv = _FusedConv(torch.randn(C, C, 3, 3) * 0.03, torch.randn(C) * 0.1, torch.bfloat16).cuda()
+    x = torch.randn(B, C, 8, 8, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    z = torch.randn_like(x).relu_()
+    want = torch.relu(torch.nn.functional.conv2d(x.float(), conv.w.float(), conv.b.float(), 1, 1) + z.float())
+    try:
+        _FusedConv.graph_fusion = False
+        two = conv(x, residual=z)
+    finally:
+        _FusedConv.graph_fusion = True
+    one = conv(x, residual=z)
+    assert any(str((B, C, 8, 8)) in k for k in _cudnn_fused.chosen_plans()), "cuDNN graph path not taken"
+    assert one.is_contiguous(memory_format=torch.channels_last) and one.dtype == torch.bfloat16
+    tol = 0.02 * float(want.abs().max())  # bf16 output rounding
+    assert float((one.float() - want).abs().max()) <= tol and float((two.float() - want).abs().max()) <= 2 * tol
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        cap = conv(x, residual=z)
+    cap.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(cap, one)
