@@ -575,6 +575,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
     a = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything else this process, its libraries (NCCL prints its
+    # version banner to stdout when NCCL_DEBUG is set) and its children write goes to stderr
+    result_out = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -597,7 +602,7 @@ def main():
             "config": {"workload": f"{a.workload}: {desc}", "net": kind, "sims_per_move": sims},
             "cpu_baseline": {"value": rate, "unit": "sims/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}), flush=True)
+            "gpu_launches": 0}), file=result_out, flush=True)
         return
 
     out, dev = run_b200(a)
@@ -622,7 +627,7 @@ def main():
                                              f"(oracle C tree/env + batch-1 torch CPU forward of the {kind} net), {wall:.1f} s wall"}
         else:
             out["cpu_baseline"] = None
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=result_out, flush=True)
 
 
 if __name__ == "__main__":
