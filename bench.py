@@ -192,6 +192,9 @@ def run_b200(a):
     iters = a.iters_per_step or sims
     args = dict(TRAIN_ARGS, num_simulations=sims)
 
+    if os.environ.get("OTH_NO_GRAPH_FUSION"):
+        from alphazero_othello_b200 import Models
+        Models._FusedConv.graph_fusion = False
     net = make_net(kind)
     # host copy of the weights (pinned), as Trainer.collect_self_play_games ships them (train.py:207-217)
     flat_host = torch.cat([p.detach().reshape(-1) for p in net.state_dict().values() if p.dtype.is_floating_point]).pin_memory()
@@ -202,7 +205,7 @@ def run_b200(a):
 
     def load_weights():  # H2D (+ NCCL broadcast from rank 0 when sharded) and re-fold in place
         flat_dev.copy_(flat_host, non_blocking=True)
-        if world > 1:
+        if world > 1 and not os.environ.get("OTH_BENCH_NO_BCAST"):
             dist.broadcast(flat_dev, 0)
         off = 0
         for p in net.state_dict().values():
@@ -216,7 +219,7 @@ def run_b200(a):
     ev = BatchedPolicy(folded, dev, torch.float32)
     eng = MctsEngine(G, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=-1, device=dev, seed=a.seed,
                      game_id_base=rank * G, game_id_stride=G * world, lanes=a.lanes, max_inline_sims=a.max_inline,
-                     out_pos_cap=G * 80, out_game_cap=G + 64)
+                     out_pos_cap=G * 160, out_game_cap=2 * G + 64)
     run = SelfPlayRunner(eng, ev, use_graph=not a.no_graph)
     run.warm_start()
 
@@ -250,8 +253,13 @@ def run_b200(a):
         dist.all_reduce(t)
         return float(t)
 
+    n_plain = [0]
+
     def plain_step():
         run.run_iterations(iters)
+        n_plain[0] += 1
+        if n_plain[0] % 32 == 0:  # long runs: finished games leave the output ring (it holds ~2 rounds of games)
+            eng.drain(to_host=False)
 
     for _ in range(a.warmup):
         plain_step()
@@ -272,10 +280,22 @@ def run_b200(a):
     pin_rootv = torch.empty((G,), dtype=torch.float64).pin_memory()
     io = {"h2d": 0, "d2h": 0}
 
+    trace = [] if os.environ.get("OTH_BENCH_E2E_TRACE") else None  # diagnosis: synchronised stage times (perturbs e2e)
+
+    def mark(tag):
+        if trace is not None:
+            torch.cuda.synchronize(dev)
+            trace.append((tag, time.perf_counter()))
+
     def e2e_step():
+        mark("start")
         load_weights()
+        if os.environ.get("OTH_BENCH_SYNC_W"):
+            torch.cuda.synchronize(dev)
+        mark("weights")
         io["h2d"] += flat_host.numel() * 4
         run.run_iterations(iters)
+        mark("iterations")
         st = eng.root_stats()
         pin_counts.copy_(st["counts"], non_blocking=True)
         pin_rootv.copy_(st["root_value"], non_blocking=True)
@@ -296,11 +316,18 @@ def run_b200(a):
                 lst = [torch.zeros_like(pay) for _ in range(world)] if rank == 0 else None
                 dist.gather(pay, lst, 0)
         torch.cuda.synchronize(dev)
+        mark("outputs")
 
     e2e_step()  # warm
+    if world > 1:  # NCCL sets up the gather's send/recv connections on first use (~0.25 s at 2 ranks, >1 s at 8): the first
+        pay = torch.zeros((1, 69), dtype=torch.float32, device=dev)  # games end at move 9, so do it before the timed region
+        dist.gather(pay, [torch.zeros_like(pay) for _ in range(world)] if rank == 0 else None, 0)
+        torch.cuda.synchronize(dev)
     io["h2d"] = io["d2h"] = 0
     ms2, d2 = timed(e2e_step, a.steps)
     e2e_value = total(d2["sims"]) / (ms2 * 1e-3)
+    if trace:
+        print(f"rank {rank} e2e stages (ms):", [(b[0], round((b[1] - a[1]) * 1e3, 1)) for a, b in zip(trace, trace[1:])], file=sys.stderr)
 
     # ---- roofline of the MCTS kernel: CUDA events around every launch, no graph
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(iters)]
