@@ -446,6 +446,25 @@ def aux_selfplay_rate(dev, workload, steps=8, warm=3):
             "positions_per_s": (c1["moves"] - c0["moves"]) / (ms * 1e-3), "steps": steps, "warmup": warm, "ms_per_step": ms / steps}
 
 
+def aux_public_api(dev, workload="c3"):
+    """The call a user of the reference makes, end to end: ``collect_self_play_games(policy, args, n_games)`` with the
+    policy's weights on the HOST, every game played to the end, the per-game lists of (int8[8,8], float32[65], float)
+    back on the host (train.py:199-225 + 136-140).  Wall clock, everything included (engine allocation, BN folding,
+    cuDNN plan selection, graph capture, ragged tail of the longest games, D2H, splitting into Python lists)."""
+    import torch
+    from alphazero_othello_b200.self_play_worker import collect_self_play_games
+    desc, kind, G, sims = WORKLOADS[workload]
+    args = dict(TRAIN_ARGS, num_simulations=sims)
+    net = make_net(kind)  # CPU module, as the trainer holds it
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    games = collect_self_play_games(net, args, G, n_slots=G, device=dev, seed=1)
+    dt = time.perf_counter() - t0
+    npos = sum(len(g) for g in games)
+    return {"workload": f"{workload}: {desc} -- {G} complete games through collect_self_play_games (host weights in, host lists out)",
+            "seconds": dt, "games": len(games), "positions": npos, "positions_per_s": npos / dt, "sims_per_s": npos * sims / dt}
+
+
 def aux_env_sharded(dev, rank, world):
     """Config C1 over all ranks: every rank rolls out its own 2^22 games (ids offset by rank); whole-job
     plies / max-over-ranks device time.  No collective on the path -- the all-reduce only gathers the timing."""
@@ -640,6 +659,7 @@ def main():
             out["aux"]["env_step_api"] = aux_env_step_api(dev)
             other = "c3" if a.workload != "c3" else "c4"  # north_star: both architectures
             out["aux"]["other_architecture"] = aux_selfplay_rate(dev, other)
+            out["aux"]["public_api_whole_games"] = aux_public_api(dev, "c3")
             import oracle
             oracle.build()
             rate, games = cpu_env_rate(cores)
