@@ -105,6 +105,7 @@ _SIGS = {
     "oth_replay_aggregate": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_int64] + [C.c_void_p] * 7),
     "oth_nn_stem_im2col_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "oth_nn_bias_add_relu_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "oth_nn_l2_discard": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -364,6 +364,26 @@ extern "C" int oth_nn_bias_add_relu_bf16(void* x, const void* res, const void* b
     return cuda_status(cudaGetLastError());
 }
 
+// Dead-activation hint: drop the (dirty) L2 lines of a buffer nobody will read again, so they are neither
+// written back to HBM nor evicted -- with a write-back each -- by the next kernel's misses.
+// discard.global.L2 works on whole 128-byte lines; the range is shrunk to line boundaries.
+__global__ void __launch_bounds__(256) k_l2_discard(char* base, long n_lines)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += stride)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + i * 128) : "memory");
+}
+
+extern "C" int oth_nn_l2_discard(void* ptr, int64_t bytes, void* stream)
+{
+    if (bytes < 0 || (bytes > 0 && !ptr)) return OTH_E_ARG;
+    uintptr_t lo = ((uintptr_t)ptr + 127) & ~(uintptr_t)127, hi = ((uintptr_t)ptr + (uintptr_t)bytes) & ~(uintptr_t)127;
+    if (hi <= lo) return OTH_OK;
+    const long n_lines = (long)((hi - lo) / 128);
+    k_l2_discard<<<grid_for(n_lines, 256), 256, 0, (cudaStream_t)stream>>>((char*)lo, n_lines);
+    return cuda_status(cudaGetLastError());
+}
+
 // canonical packed boards [n][2] -> int8 [n,64] (+1 own / -1 opp)
 extern "C" int oth_unpack_canonical(const uint64_t* boards, int8_t* states, int64_t n, void* stream)
 {

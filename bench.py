@@ -192,6 +192,9 @@ def run_b200(a):
     iters = a.iters_per_step or sims
     args = dict(TRAIN_ARGS, num_simulations=sims)
 
+    if os.environ.get("OTH_L2_DISCARD"):  # A/B: off | tail | all
+        from alphazero_othello_b200 import Models
+        Models.FoldedNet.l2_discard = {"off": None}.get(os.environ["OTH_L2_DISCARD"], os.environ["OTH_L2_DISCARD"])
     if os.environ.get("OTH_NO_GRAPH_FUSION"):
         from alphazero_othello_b200 import Models
         Models._FusedConv.graph_fusion = False

@@ -326,6 +326,13 @@ int oth_nn_bias_add_relu_bf16(void* x, const void* res, const void* bias, int64_
  * stem runs as one GEMM with a fused bias+ReLU epilogue and writes channels-last output. */
 int oth_nn_stem_im2col_bf16(const float* planes, void* cols, int64_t n, void* stream);
 
+/* Network boundary helper: tells L2 that [ptr, ptr+bytes) is dead (an activation buffer whose last
+ * consumer has run, e.g. the trunk output once the head GEMM has read it -- Models.py:213-219): its
+ * cached lines are dropped without write-back (PTX discard.global.L2, whole 128-byte lines inside the
+ * range only).  The contents of the range are undefined afterwards.  Must follow the last reader and
+ * precede the next writer in stream order. */
+int oth_nn_l2_discard(void* ptr, int64_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
