@@ -68,3 +68,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(d, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_cudnn_graph_path_declines_cpu_and_small_batches():
+    """The fused residual convolution is an optimisation of the network twin only: without a CUDA bf16
+    batch of >= 256 it returns None and the caller keeps its two-kernel path."""
+    import torch
+    from alphazero_othello_b200 import _cudnn_fused
+    x = torch.zeros(512, 8, 8, 8, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = torch.zeros(8, 8, 3, 3, dtype=torch.bfloat16)
+    assert _cudnn_fused.conv_res_bias_relu(x, w, torch.zeros(8, dtype=torch.bfloat16), x) is None
+    assert _cudnn_fused.conv_res_bias_relu(x.float(), w.float(), torch.zeros(8), x.float()) is None
+    assert _cudnn_fused.chosen_plans() == {}
