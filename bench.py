@@ -222,7 +222,7 @@ def run_b200(a):
     ev = BatchedPolicy(folded, dev, torch.float32)
     eng = MctsEngine(G, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=-1, device=dev, seed=a.seed,
                      game_id_base=rank * G, game_id_stride=G * world, lanes=a.lanes, max_inline_sims=a.max_inline,
-                     out_pos_cap=G * 160, out_game_cap=2 * G + 64)
+                     out_pos_cap=G * 160, out_game_cap=2 * G + 64, node_cap=a.node_cap or None)
     run = SelfPlayRunner(eng, ev, use_graph=not a.no_graph)
     run.warm_start()
 
@@ -620,6 +620,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=8)
     ap.add_argument("--max-inline", type=int, default=8)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--node-cap", type=int, default=0, help="experiment: arena size per slot (default 48*sims+1024)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
