@@ -149,6 +149,20 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+NET_FLOP_PER_EVAL = {"big": 188.99e6, "small": 15.29e6}  # forward MACs x 2 per position
+
+
+def network_roofline(kind, evals_per_s):
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, src = 1370.8, "fallback"
+    if os.path.exists(p):
+        d = json.load(open(p))
+        peak, src = float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", peak))), "measured sustained (MEASURED_PEAKS.json)"
+    ach = evals_per_s * NET_FLOP_PER_EVAL[kind] / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": src,
+            "what": "policy/value network forward (cuDNN/cuBLAS via PyTorch, outside this repo's kernels): evaluations/s x FLOP per evaluation"}
+
+
 def algorithmic_bytes(d, n_slots, launches):
     """HBM bytes the MCTS kernel must move for the work the counters record (DESIGN.md 'Kernel roofline')."""
     depth_nodes = d["levels"] + d["sims"]            # path entries = levels descended + the root of every simulation
@@ -275,6 +289,7 @@ def run_b200(a):
     eng.raise_on_error()
     sims_total = total(d["sims"])
     moves_total = total(d["moves"])
+    evals_total = total(d["evals"])
     value = sims_total / (ms * 1e-3)
     eng.drain(to_host=False)
 
@@ -407,6 +422,8 @@ def run_b200(a):
                          "random_access": {"peak": rnd_gbs.value, "unit": "GB/s", "frac": achieved / rnd_gbs.value if rnd_gbs.value else None,
                                            "how": f"measured live: independent random 64-byte reads over {foot >> 20} MiB (oth_host_random_read_probe)"},
                          "kernel_share_of_iteration": k_avg / (ms / a.steps / iters)},
+            # the step's dominant cost is the (library) network: its share of the dense bf16 peak sustained by cuBLAS on this pool
+            "network_roofline": network_roofline(kind, evals_total / (ms * 1e-3)),
             "search_counters_per_step": {k: d[k] / a.steps for k in ("sims", "evals", "terminal_sims", "moves", "games", "nodes", "copied", "levels", "children")},
         }
     if world > 1:
