@@ -152,12 +152,13 @@ def measured_peaks():
 NET_FLOP_PER_EVAL = {"big": 188.99e6, "small": 15.29e6}  # forward MACs x 2 per position
 
 
-def network_roofline(kind, evals_per_s):
+def network_roofline(kind, evals_per_s, n_gpus=1):
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak, src = 1370.8, "fallback"
     if os.path.exists(p):
         d = json.load(open(p))
         peak, src = float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", peak))), "measured sustained (MEASURED_PEAKS.json)"
+    peak *= n_gpus
     ach = evals_per_s * NET_FLOP_PER_EVAL[kind] / 1e12
     return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": src,
             "what": "policy/value network forward (cuDNN/cuBLAS via PyTorch, outside this repo's kernels): evaluations/s x FLOP per evaluation"}
@@ -423,7 +424,7 @@ def run_b200(a):
                                            "how": f"measured live: independent random 64-byte reads over {foot >> 20} MiB (oth_host_random_read_probe)"},
                          "kernel_share_of_iteration": k_avg / (ms / a.steps / iters)},
             # the step's dominant cost is the (library) network: its share of the dense bf16 peak sustained by cuBLAS on this pool
-            "network_roofline": network_roofline(kind, evals_total / (ms * 1e-3)),
+            "network_roofline": network_roofline(kind, evals_total / (ms * 1e-3), world),
             "search_counters_per_step": {k: d[k] / a.steps for k in ("sims", "evals", "terminal_sims", "moves", "games", "nodes", "copied", "levels", "children")},
         }
     if world > 1:
