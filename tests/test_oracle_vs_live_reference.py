@@ -1,0 +1,155 @@
+"""Differential pinning of the oracle against the LIVE reference (dev container only).
+
+tests/golden/ holds results of the reference that travel to the GPU box; here, where
+/root/reference exists, the oracle is additionally driven side by side with the reference's own
+classes on fresh random inputs (other seeds, stubs and hyper-parameters than the goldens).  Skipped
+wherever the reference is absent.  Nothing is copied: the reference is imported and called.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REF = os.environ.get("OTHELLO_REFERENCE", "/root/reference")
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "envs", "othello.py")),
+                                reason="reference checkout not present (GPU box)")
+
+M64 = (1 << 64) - 1
+
+
+@pytest.fixture(scope="module")
+def ref():
+    sys.dont_write_bytecode = True
+    added = REF not in sys.path
+    if added:
+        sys.path.insert(0, REF)
+    mine = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "envs" or k.startswith("envs.")}  # not this repo's envs
+    try:
+        from envs.othello import OthelloGameNew
+        from MCTS_model import MCTS
+        yield {"Game": OthelloGameNew, "MCTS": MCTS}
+    finally:
+        for k in [k for k in sys.modules if k == "envs" or k.startswith("envs.") or k == "MCTS_model"]:
+            sys.modules.pop(k)
+        sys.modules.update(mine)
+        if added:
+            sys.path.remove(REF)
+
+
+def _mix(x):
+    x &= M64
+    x ^= x >> 31
+    x = (x * 0x9E3779B97F4A7C15) & M64
+    x ^= x >> 29
+    return x
+
+
+class HashStub:
+    """Deterministic policy: float32 priors and a value in [-1, 1] from a hash of (player*state, salt)."""
+
+    def __init__(self, salt):
+        self.salt = salt
+
+    def inference(self, state, player):
+        h = _mix(int.from_bytes((np.asarray(state) * int(player)).astype(np.int8).tobytes(), "little") % M64 ^ self.salt)
+        raw = np.array([1 + (_mix(h + 977 * a) % 97) for a in range(65)], dtype=np.float32)
+        return raw / raw.sum(), float(np.float32(int(_mix(h ^ 0xABCDEF) % 401) - 200) / np.float32(200))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_env_random_games_side_by_side(ref, seed):
+    """Ten random games per seed: masks, next states, terminal tests (both players), scores, illegal moves."""
+    import oracle as O
+    g, o = ref["Game"](8), O.OracleGame()
+    rs = np.random.RandomState(1000 + seed)
+    for _ in range(10):
+        s, player = g.get_initial_state(), 1
+        assert np.array_equal(s, o.get_initial_state())
+        for ply in range(130):
+            m = g.get_valid_moves(s, player)
+            assert np.array_equal(m, o.get_valid_moves(s, player))
+            for p in (player, -player):
+                assert g.get_value_and_terminated(s, None, p) == o.get_value_and_terminated(s, None, p)
+                assert g.get_score(s, p) == o.get_score(s, p)
+            if ply % 7 == 0:  # illegal actions raise in both
+                for a in rs.choice(np.nonzero(m[:64] == 0)[0], 3):
+                    with pytest.raises(ValueError):
+                        g.get_next_state(s, int(a), player)
+                    with pytest.raises(ValueError):
+                        o.get_next_state(s, int(a), player)
+            a = int(rs.choice(np.nonzero(m)[0]))
+            ns = g.get_next_state(s, a, player)
+            assert np.array_equal(ns, o.get_next_state(s, a, player)) and ns.dtype == np.int8
+            s = ns
+            if g.get_value_and_terminated(s, a, player)[1]:
+                break
+            player = -player
+        else:
+            raise AssertionError("game did not end")
+
+
+CASES = [  # salt, sims, c_puct, eps, alpha, temp, moves
+    (1, 30, 2.0, 0.0, 1.0, 1.0, 6),
+    (2, 57, 1.0, 0.3, 1.0, 1.0, 5),
+    (3, 25, 3.5, 0.25, 0.3, 0.5, 8),
+    (4, 80, 2.0, 0.3, 0.03, 1.0, 4),
+    (5, 16, 0.7, 0.5, 1.0, 2.0, 10),
+    (6, 40, 2.0, 0.3, 1.0, 0.0, 8),
+]
+
+
+@pytest.mark.parametrize("salt,sims,c_puct,eps,alpha,temp,moves", CASES)
+def test_mcts_side_by_side(ref, monkeypatch, salt, sims, c_puct, eps, alpha, temp, moves):
+    """Reference MCTS (num_threads=1) and the oracle on the same stub, the same Dirichlet draws and the same
+    moves, with tree re-use: child visit counts, child values / priors, root value / N bit for bit; policy
+    targets bit for bit at temp 1 and within 1e-6 otherwise."""
+    import oracle as O
+    stub = HashStub(salt)
+    g = ref["Game"](8)
+    drawn, ties = [], []
+    real_dirichlet, real_choice = np.random.dirichlet, np.random.choice
+
+    def dirichlet(a, *k, **kw):
+        drawn.append(real_dirichlet(a, *k, **kw))
+        return drawn[-1]
+
+    def choice(a, *k, **kw):  # tie pick at temp ~ 0 (MCTS_model.py:249-255): take the first, tell the oracle u = 0
+        if "p" not in kw and not k and np.ndim(a) == 1:
+            ties.append(len(a))
+            return a[0]
+        return real_choice(a, *k, **kw)
+
+    monkeypatch.setattr(np.random, "dirichlet", dirichlet)
+    monkeypatch.setattr(np.random, "choice", choice)
+    np.random.seed(salt)
+    m = ref["MCTS"](g, {"c_puct": c_puct, "num_simulations": sims, "num_threads": 1}, stub, dirichlet_alpha=alpha,
+                    dirichlet_epsilon=eps)
+    om = O.OracleMCTS(c_puct, sims, O.Evaluator(fn=stub.inference), dirichlet_epsilon=eps)
+    s, player = g.get_initial_state(), 1
+    rs = np.random.RandomState(77 + salt)
+    for mv in range(moves):
+        n0 = len(drawn)
+        probs = m.policy_improve_step(s, player, temp=temp)
+        noise = drawn[-1] if len(drawn) > n0 else None
+        oprobs = om.policy_improve_step(s, player, temp=temp, noise=noise, u_tie=0.0)
+        st = om.root_stats()
+        counts = np.zeros(65, np.int32)
+        cval, cpri = np.zeros(65), np.zeros(65)
+        for a, ch in m.root.children.items():
+            counts[a], cval[a], cpri[a] = ch.visit_count, ch.value, float(ch.prior)
+        assert np.array_equal(counts, st["counts"]), mv
+        assert np.array_equal(cval, st["child_value"]) and np.array_equal(cpri, st["child_prior"]), mv
+        assert m.root.value == st["root_value"] and m.root.visit_count == st["root_n"], mv
+        assert probs.dtype == np.float32
+        if temp == 1.0 or temp == 0.0:
+            assert np.array_equal(probs, oprobs), mv
+        else:
+            assert np.abs(probs - oprobs).max() <= 1e-6, mv
+        a = int(rs.choice(65, p=probs.astype(np.float64) / probs.astype(np.float64).sum()))
+        m.make_move(a)
+        om.make_move(a)
+        s = g.get_next_state(s, a, player)
+        if g.get_value_and_terminated(s, a, player)[1]:
+            break
+        player = -player
