@@ -440,3 +440,42 @@ def test_full_size_c4_whole_games_invariants_and_sampled_oracle_replay():
         assert np.array_equal(states[first:first + T], ref["states"]), g
         assert np.array_equal(pis_h[first:first + T], ref["pis"]), g
         assert np.array_equal(v_h[first:first + T], ref["values"]), g
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("OTH_FUZZ_SEEDS", "10"))))  # more seeds: one-off fuzz runs
+def test_randomised_hyper_parameters_vs_oracle(seed):
+    """Differential fuzz: random c_puct / simulations / Dirichlet eps, alpha / temperature / exploratory moves / lambda /
+    lane width / inline-simulation budget; 24 concurrent games on the engine's own randomness, every game replayed
+    through the oracle.  Bit-exact states, value targets and (temperature 1 or ~0) policy targets; 1e-6 otherwise."""
+    import oracle as O
+    from alphazero_othello_b200.engine import split_games
+    rs = np.random.RandomState(4242 + seed)
+    temp = float(rs.choice([0.25, 0.5, 1.0, 1.0, 2.0]))
+    args = {"c_puct": float(rs.uniform(0.5, 4.0)), "num_simulations": int(rs.choice([1, 2, 7, 33, 64, 120])),
+            "dirichlet_alpha": float(rs.choice([0.03, 0.3, 1.0])), "dirichlet_epsilon": float(rs.choice([0.0, 0.1, 0.3, 0.6])),
+            "mcts_temperature": temp, "num_exploratory_moves": int(rs.randint(0, 41)), "lambda": float(rs.uniform(0.5, 1.0))}
+    lanes = int(rs.choice(LANES))
+    salt = int(rs.randint(1, 1 << 30))
+    n = 24
+    e = _selfplay_engine(args, lanes, n, False, salt, seed=int(rs.randint(1 << 30)), max_inline_sims=int(rs.choice([1, 4, 16, 1000])))
+    _run_to_done(e, max_launches=60000)
+    noise = e.noise.cpu().numpy(); um = e.u_move.cpu().numpy(); ut = e.u_tie.cpu().numpy()
+    out = e.drain()
+    games = split_games(out)
+    assert sorted(int(g[0]) for g in out["games"].numpy()) == list(range(n))
+    c = e.counters()
+    assert c["games"] == n and c["errors"] == 0
+    tot_sims = 0
+    for g in range(n):
+        ref = O.self_play(args, O.Evaluator(stub=O.STUB_H, salt=salt), noise[g], um[g], ut[g])
+        traj = games[g]
+        assert len(traj) == len(ref["values"]), (args, g)
+        assert np.array_equal(np.stack([t[0] for t in traj]), ref["states"]), (args, g)
+        pis = np.stack([t[1] for t in traj])
+        if temp == 1.0:
+            assert np.array_equal(pis, ref["pis"]), (args, g)
+        else:
+            assert np.abs(pis - ref["pis"]).max() <= 1e-6, (args, g)
+        assert np.array_equal(np.array([t[2] for t in traj]), ref["values"]), (args, g)
+        tot_sims += ref["counters"]["sims"]
+    assert c["sims"] == tot_sims
