@@ -99,6 +99,8 @@ _SIGS = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "oth_mcts_advance": (C.c_int, [C.c_void_p] * 4),
     "oth_mcts_poll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "oth_mcts_profile_begin": (C.c_int, [C.c_int32]),
+    "oth_mcts_profile_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "oth_mcts_root_stats": (C.c_int, [C.c_void_p] * 9),
     "oth_unpack_canonical": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "oth_replay_aggregate_workspace_bytes": (C.c_int, [C.c_int64, C.c_void_p]),

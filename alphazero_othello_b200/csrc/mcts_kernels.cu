@@ -1542,6 +1542,63 @@ extern "C" int oth_mcts_begin_search(const oth_mcts_config* cfg, const oth_mcts_
     return oth_mcts_begin_search_masked(cfg, b, nullptr, stream);
 }
 
+// ---- per-launch kernel timing (oth_mcts_profile_begin / _end): CUDA events recorded on the launching stream
+// around the step kernel and around the move kernel, so a bench can time each of them inside its pipeline.
+namespace {
+struct LaunchProfile {
+    cudaEvent_t* ev = nullptr;  // 3 per launch: before step, after step, after move
+    int cap = 0, n = 0;
+    bool on = false;
+} g_prof;
+
+inline bool prof_mark(int which, void* stream)
+{
+    if (!g_prof.on || g_prof.n >= g_prof.cap) return false;
+    cudaEventRecord(g_prof.ev[3 * g_prof.n + which], (cudaStream_t)stream);
+    return true;
+}
+}  // namespace
+
+extern "C" int oth_mcts_profile_begin(int32_t max_launches)
+{
+    if (max_launches <= 0 || max_launches > (1 << 20)) return OTH_E_ARG;
+    if (g_prof.ev) {
+        for (int i = 0; i < 3 * g_prof.cap; i++) cudaEventDestroy(g_prof.ev[i]);
+        delete[] g_prof.ev;
+        g_prof.ev = nullptr;
+    }
+    g_prof.ev = new cudaEvent_t[3 * (size_t)max_launches];
+    for (int i = 0; i < 3 * max_launches; i++)
+        if (cudaEventCreate(&g_prof.ev[i]) != cudaSuccess) return cuda_status(cudaGetLastError());
+    g_prof.cap = max_launches;
+    g_prof.n = 0;
+    g_prof.on = true;
+    return OTH_OK;
+}
+
+extern "C" int oth_mcts_profile_end(float* step_ms, float* move_ms, int32_t* n_launches)
+{
+    if (!g_prof.ev || !n_launches) return OTH_E_ARG;
+    g_prof.on = false;
+    const int n = g_prof.n;
+    int rc = OTH_OK;
+    for (int i = 0; i < n && rc == OTH_OK; i++) {
+        if (cudaEventSynchronize(g_prof.ev[3 * i + 2]) != cudaSuccess) rc = cuda_status(cudaGetLastError());
+        float a = 0.f, c = 0.f;
+        if (rc == OTH_OK && (cudaEventElapsedTime(&a, g_prof.ev[3 * i], g_prof.ev[3 * i + 1]) != cudaSuccess ||
+                             cudaEventElapsedTime(&c, g_prof.ev[3 * i + 1], g_prof.ev[3 * i + 2]) != cudaSuccess))
+            rc = cuda_status(cudaGetLastError());
+        if (step_ms) step_ms[i] = a;
+        if (move_ms) move_ms[i] = c;
+    }
+    *n_launches = n;
+    for (int i = 0; i < 3 * g_prof.cap; i++) cudaEventDestroy(g_prof.ev[i]);
+    delete[] g_prof.ev;
+    g_prof.ev = nullptr;
+    g_prof.cap = g_prof.n = 0;
+    return rc;
+}
+
 extern "C" int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const float* priors, const float* values,
                              float* nn_input, void* stream)
 {
@@ -1552,15 +1609,22 @@ extern "C" int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers*
     p.priors = priors;
     p.values = values;
     p.nn_input = nn_input;
+    const bool prof = prof_mark(0, stream);
     if (cfg->eval_kind != OTH_EVAL_EXTERNAL) {
         LAUNCH_LANES(k_mcts_step_stub, mcts_grid(cfg), stream, p);
+        if (prof) prof_mark(1, stream);
     } else {
         LAUNCH_LANES(k_mcts_step, mcts_grid(cfg), stream, p);
+        if (prof) prof_mark(1, stream);
         if (cfg->self_play) {
             const int warps = (cfg->n_slots + 31) / 32;
             const int blocks = (warps + kBlock / 32 - 1) / (kBlock / 32);
             k_mcts_move<<<blocks < sm_count() * 4 ? blocks : sm_count() * 4, kBlock, 0, (cudaStream_t)stream>>>(p);
         }
+    }
+    if (prof) {
+        prof_mark(2, stream);
+        g_prof.n++;
     }
     return cuda_status(cudaGetLastError());
 }
@@ -1583,11 +1647,17 @@ extern "C" int oth_mcts_step_fused(const oth_mcts_config* cfg, const oth_mcts_bu
     p.priors_out = priors_out;
     p.values_out = values_out;
     p.nn_input = nn_input;
+    const bool prof = prof_mark(0, stream);
     LAUNCH_LANES(k_mcts_step_fused, mcts_grid(cfg), stream, p);
+    if (prof) prof_mark(1, stream);
     if (cfg->self_play) {
         const int warps = (cfg->n_slots + 31) / 32;
         const int blocks = (warps + kBlock / 32 - 1) / (kBlock / 32);
         k_mcts_move<<<blocks < sm_count() * 4 ? blocks : sm_count() * 4, kBlock, 0, (cudaStream_t)stream>>>(p);
+    }
+    if (prof) {
+        prof_mark(2, stream);
+        g_prof.n++;
     }
     return cuda_status(cudaGetLastError());
 }

@@ -164,8 +164,9 @@ def network_roofline(kind, evals_per_s, n_gpus=1):
             "what": "policy/value network forward (cuDNN/cuBLAS via PyTorch, outside this repo's kernels): evaluations/s x FLOP per evaluation"}
 
 
-def algorithmic_bytes(d, n_slots, launches):
-    """HBM bytes the MCTS kernel must move for the work the counters record (DESIGN.md 'Kernel roofline')."""
+def algorithmic_bytes(d, n_slots, launches, kernel="both"):
+    """HBM bytes the MCTS kernels must move for the work the counters record (DESIGN.md 'Kernel roofline'):
+    kernel = "step" (k_mcts_step), "move" (k_mcts_move: policy target, re-rooting copy) or "both"."""
     depth_nodes = d["levels"] + d["sims"]            # path entries = levels descended + the root of every simulation
     b = 0
     b += 32 * d["children"]                          # select: child records scanned (2 x 128-bit per child)
@@ -175,9 +176,13 @@ def algorithmic_bytes(d, n_slots, launches):
     b += d["evals"] * (16 + 16 + 32 + 8)             # leaf board (select + expand), leaf record, first_child/meta update
     b += d["evals"] * (256 + 260 + 4)                # network input plane written, priors + value read
     b += 48 * d["nodes"]                             # expansion: child record + child board written
-    b += (48 + 48) * d["copied"]                     # re-root: kept subtree read and written
-    b += d["moves"] * (32 * 12 + 260 + 32 + 16)      # policy target: root children, trajectory row
     b += 2 * 64 * n_slots * launches                 # per-slot control block read and written every launch
+    if kernel in ("both", "move"):
+        mv = (48 + 48) * d["copied"]                 # re-root: kept subtree read and written
+        mv += d["moves"] * (32 * 12 + 260 + 32 + 16)  # policy target: root children, trajectory row
+        if kernel == "move":
+            return mv + n_slots * launches           # + the move-flag byte per slot per launch
+        b += mv
     return b
 
 
@@ -348,36 +353,41 @@ def run_b200(a):
     if trace:
         print(f"rank {rank} e2e stages (ms):", [(b[0], round((b[1] - a[1]) * 1e3, 1)) for a, b in zip(trace, trace[1:])], file=sys.stderr)
 
-    # ---- roofline of the MCTS kernel: CUDA events around every launch, no graph
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(iters)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(iters)]
+    # ---- roofline of the MCTS kernels: the library records CUDA events around the step kernel and around the
+    # move kernel of every launch (oth_mcts_profile_begin/_end), same pipeline, no graph
+    import ctypes as C
     torch.cuda.synchronize(dev)
     c0 = eng.counters()
+    gap_cycles = int(float(os.environ.get("OTH_BENCH_GAP_US", "0")) * 1400)
+    _lib.check(_lib.lib().oth_mcts_profile_begin(iters))
     for i in range(iters):
         if run.fused:  # same launch as in the timed region: softmax / tanh fused into the step kernel
             lg, vp = ev.raw(eng.nn_input)
-            ev0[i].record()
+            if gap_cycles:  # experiment: idle gap between the network and the step kernel
+                torch.cuda._sleep(gap_cycles)
             eng.step_fused(lg, vp)
-            ev1[i].record()
         else:
             ev(eng.nn_input, eng.priors, eng.values)
-            ev0[i].record()
             eng.step()
-            ev1[i].record()
+    step_ms, move_ms, n_rec = (C.c_float * iters)(), (C.c_float * iters)(), C.c_int32(0)
+    _lib.check(_lib.lib().oth_mcts_profile_end(step_ms, move_ms, C.byref(n_rec)))
     torch.cuda.synchronize(dev)
+    assert n_rec.value == iters
     c1 = eng.counters()
     dk = {k: c1[k] - c0[k] for k in c1}
-    kms_seq = [x.elapsed_time(y) for x, y in zip(ev0, ev1)]
+    kms_seq, mms_seq = list(step_ms), list(move_ms)
     if os.environ.get("OTH_BENCH_DUMP_LAUNCHES"):
-        json.dump(kms_seq, open(os.environ["OTH_BENCH_DUMP_LAUNCHES"], "w"))
+        json.dump({"step_ms": kms_seq, "move_ms": mms_seq}, open(os.environ["OTH_BENCH_DUMP_LAUNCHES"], "w"))
     kms = sorted(kms_seq)
     k_avg = sum(kms) / len(kms)
-    alg = algorithmic_bytes(dk, G, iters) / iters
+    alg = algorithmic_bytes(dk, G, iters, "step") / iters
     peak, peak_src = measured_peaks()
     achieved = alg / (k_avg * 1e-3) / 1e9
+    mms = sorted(mms_seq)
+    m_avg = sum(mms) / len(mms)
+    alg_move = algorithmic_bytes(dk, G, iters, "move") / iters
     # what HBM delivers for the tree's access pattern: independent random 64-byte reads over a
     # footprint the size of the arenas (row-activation / TLB bound, far below the streaming copy peak)
-    import ctypes as C
     rnd_gbs, rnd_ms = C.c_double(0), C.c_float(0)
     foot = min(max(eng.buf_bytes[0] + eng.buf_bytes[1], 1 << 30), 24 << 30)
     if _lib.lib().oth_host_random_read_probe(foot, 64, C.byref(rnd_gbs), C.byref(rnd_ms)) != 0:
@@ -403,8 +413,9 @@ def run_b200(a):
                        "sharding": "games by id, no collective on the search path",
                        "network_twin": {"residual_conv": "one cuDNN graph relu(bias(conv+residual)) per block" if fused_plans
                                         else "cuDNN conv + k_bias_add_relu_bf16", "cudnn_plans": fused_plans},
-                       "roofline_timing": "CUDA events around every oth_mcts_step launch (k_mcts_step + k_mcts_move) in an un-graphed "
-                                          "pass of iters_per_step iterations of the same pipeline right after the timed region "
+                       "roofline_timing": "CUDA events recorded by the library on the launching stream around k_mcts_step and around "
+                                          "k_mcts_move of every launch (oth_mcts_profile_begin/_end) in an un-graphed pass of "
+                                          "iters_per_step iterations of the same pipeline right after the timed region "
                                           "(events cannot be recorded inside the replayed graph)"},
             "positions_per_s": moves_total / (ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": "sims/s", "h2d_bytes_per_step": io["h2d"] // a.steps,
@@ -415,14 +426,18 @@ def run_b200(a):
             # residual convolutions do not run as one cuDNN graph -- one k_bias_add_relu_bf16 per residual block
             "gpu_launches": a.steps * iters * (3 + (0 if fused_plans else (5 if kind == "big" else 1))),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": f"k_mcts_step{'_fused' if run.fused else ''}<{a.lanes}> (+ k_mcts_move)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": f"k_mcts_step{'_fused' if run.fused else ''}<{a.lanes}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg, "launch_ms_avg": k_avg, "launch_ms_median": kms[len(kms) // 2], "launch_ms_max": kms[-1],
                          "launch_ms_p90": kms[int(len(kms) * 0.9)],
                          "bytes_per_sim": algorithmic_bytes(dk, G, iters) / max(dk["sims"], 1),
                          "random_access": {"peak": rnd_gbs.value, "unit": "GB/s", "frac": achieved / rnd_gbs.value if rnd_gbs.value else None,
                                            "how": f"measured live: independent random 64-byte reads over {foot >> 20} MiB (oth_host_random_read_probe)"},
-                         "kernel_share_of_iteration": k_avg / (ms / a.steps / iters)},
+                         "move_kernel": {"kernel": "k_mcts_move (policy target, move sampling, re-rooting copy, game hand-off)",
+                                         "launch_ms_avg": m_avg, "launch_ms_median": mms[len(mms) // 2], "launch_ms_max": mms[-1],
+                                         "algorithmic_bytes_per_launch": alg_move,
+                                         "achieved": alg_move / (m_avg * 1e-3) / 1e9, "frac": alg_move / (m_avg * 1e-3) / 1e9 / peak},
+                         "kernel_share_of_iteration": (k_avg + m_avg) / (ms / a.steps / iters)},
             # the step's dominant cost is the (library) network: its share of the dense bf16 peak sustained by cuBLAS on this pool
             "network_roofline": network_roofline(kind, evals_total / (ms * 1e-3), world),
             "search_counters_per_step": {k: d[k] / a.steps for k in ("sims", "evals", "terminal_sims", "moves", "games", "nodes", "copied", "levels", "children")},

@@ -284,6 +284,14 @@ int oth_mcts_step_fused(const oth_mcts_config* cfg, const oth_mcts_buffers* b, c
                         const void* value_preact, int64_t value_stride, int32_t is_bf16, float* priors_out, float* values_out,
                         float* nn_input, void* stream);
 
+/* Per-launch kernel timing for benches (not thread-safe, one profile at a time): between _begin and _end every
+ * oth_mcts_step / oth_mcts_step_fused call records CUDA events on its stream before the step kernel, after it and
+ * after the move kernel (up to max_launches calls; do not use while the stream is being captured into a graph).
+ * _end waits for the recorded launches and writes their durations in milliseconds: step_ms[i] = the step kernel,
+ * move_ms[i] = the move kernel of call i (either may be NULL); *n_launches = calls recorded. */
+int oth_mcts_profile_begin(int32_t max_launches);
+int oth_mcts_profile_end(float* step_ms, float* move_ms, int32_t* n_launches);
+
 /* Refresh OTH_BUF_COUNTERS: sums the per-slot event counters and derives the gauges (WAITING /
  * ACTIVE / ERRORS / MAX_TOP) from the control blocks.  Kept out of the hot kernel; hosts call
  * it when they want totals or need to know whether to stop. */
