@@ -479,3 +479,27 @@ def test_randomised_hyper_parameters_vs_oracle(seed):
         assert np.array_equal(np.array([t[2] for t in traj]), ref["values"]), (args, g)
         tot_sims += ref["counters"]["sims"]
     assert c["sims"] == tot_sims
+
+
+def test_launch_profile_records_step_and_move_kernels():
+    """oth_mcts_profile_begin/_end: one (step, move) duration pair per oth_mcts_step call, recording stops at the cap."""
+    import ctypes as C
+    from alphazero_othello_b200 import _lib
+    args = {"c_puct": 2.0, "num_simulations": 8, "dirichlet_alpha": 1.0, "dirichlet_epsilon": 0.3,
+            "mcts_temperature": 1.0, "num_exploratory_moves": 10, "lambda": 0.98}
+    from alphazero_othello_b200.engine import MctsEngine
+    e = MctsEngine(64, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=1)
+    e.priors.fill_(1.0 / 65)
+    e.reset()
+    L = _lib.lib()
+    assert L.oth_mcts_profile_begin(0) == _lib.lib().oth_mcts_profile_begin(-3) != 0  # argument check
+    _lib.check(L.oth_mcts_profile_begin(5))
+    for _ in range(7):
+        e.step()
+    step_ms, move_ms, n = (C.c_float * 5)(), (C.c_float * 5)(), C.c_int32(-1)
+    _lib.check(L.oth_mcts_profile_end(step_ms, move_ms, C.byref(n)))
+    assert n.value == 5
+    assert all(0.0 < t < 50.0 for t in step_ms) and all(0.0 < t < 50.0 for t in move_ms)
+    assert L.oth_mcts_profile_end(step_ms, move_ms, C.byref(n)) != 0  # nothing to end
+    e.step()  # launches keep working with profiling off
+    e.raise_on_error()
