@@ -34,6 +34,7 @@ using namespace oth;
 namespace {
 
 constexpr int kBlock = 128;
+constexpr int kMoveSet = 8;  // slots per warp in k_mcts_move
 constexpr uint64_t kSaltNoise = 0x6e6f697365ULL;  // Philox purposes
 constexpr uint32_t kPurposeMove = 1, kPurposeTie = 2;
 constexpr uint64_t kSaltRollout = 0x726f6c6c6f7574ULL;
@@ -1209,14 +1210,16 @@ __global__ void __launch_bounds__(kBlock) k_mcts_move(const Params P)
     Ctx<32> ctx(tile, P, scratch[threadIdx.x / 32]);
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * kBlock) / 32;
-    const int n_sets = (P.cfg.n_slots + 31) / 32;
+    // a warp owns kMoveSet consecutive slots: small sets so that the launch in which every slot re-roots at once
+    // (one per move while the games are in step) spreads over ~2 000 warps instead of 512
+    const int n_sets = (P.cfg.n_slots + kMoveSet - 1) / kMoveSet;
     for (int w = (blockIdx.x * kBlock + threadIdx.x) / 32; w < n_sets; w += warps) {
-        const int s0 = w * 32 + lane;
-        unsigned m = __ballot_sync(0xffffffffu, s0 < P.cfg.n_slots && P.move_flags[s0] != 0);
+        const int s0 = w * kMoveSet + lane;
+        unsigned m = __ballot_sync(0xffffffffu, lane < kMoveSet && s0 < P.cfg.n_slots && P.move_flags[s0] != 0);
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
-            ctx.slot = w * 32 + b;
+            ctx.slot = w * kMoveSet + b;
             ctx.template run_slot<true, false>();
             if (lane == 0) P.move_flags[ctx.slot] = 0;
             __syncwarp();
@@ -1460,6 +1463,14 @@ int mcts_grid(const oth_mcts_config* cfg)
     return (int)(need < full ? need : full);
 }
 
+// k_mcts_move: one warp per set of kMoveSet slots, at most 4 resident blocks' worth per SM (162 registers)
+inline int move_grid(const oth_mcts_config* cfg)
+{
+    const int warps = (cfg->n_slots + kMoveSet - 1) / kMoveSet;
+    const int blocks = (warps + kBlock / 32 - 1) / (kBlock / 32);
+    return blocks < sm_count() * 4 ? blocks : sm_count() * 4;
+}
+
 #define LAUNCH_LANES(kernel, grid, stream, ...)                                              \
     do {                                                                                     \
         if (cfg->lanes == 32) kernel<32><<<grid, kBlock, 0, (cudaStream_t)stream>>>(__VA_ARGS__); \
@@ -1617,9 +1628,7 @@ extern "C" int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers*
         LAUNCH_LANES(k_mcts_step, mcts_grid(cfg), stream, p);
         if (prof) prof_mark(1, stream);
         if (cfg->self_play) {
-            const int warps = (cfg->n_slots + 31) / 32;
-            const int blocks = (warps + kBlock / 32 - 1) / (kBlock / 32);
-            k_mcts_move<<<blocks < sm_count() * 4 ? blocks : sm_count() * 4, kBlock, 0, (cudaStream_t)stream>>>(p);
+            k_mcts_move<<<move_grid(cfg), kBlock, 0, (cudaStream_t)stream>>>(p);
         }
     }
     if (prof) {
@@ -1651,9 +1660,7 @@ extern "C" int oth_mcts_step_fused(const oth_mcts_config* cfg, const oth_mcts_bu
     LAUNCH_LANES(k_mcts_step_fused, mcts_grid(cfg), stream, p);
     if (prof) prof_mark(1, stream);
     if (cfg->self_play) {
-        const int warps = (cfg->n_slots + 31) / 32;
-        const int blocks = (warps + kBlock / 32 - 1) / (kBlock / 32);
-        k_mcts_move<<<blocks < sm_count() * 4 ? blocks : sm_count() * 4, kBlock, 0, (cudaStream_t)stream>>>(p);
+        k_mcts_move<<<move_grid(cfg), kBlock, 0, (cudaStream_t)stream>>>(p);
     }
     if (prof) {
         prof_mark(2, stream);
