@@ -153,3 +153,84 @@ def test_mcts_side_by_side(ref, monkeypatch, salt, sims, c_puct, eps, alpha, tem
         if g.get_value_and_terminated(s, a, player)[1]:
             break
         player = -player
+
+
+class _RngTap:
+    """Logs what the reference draws from np.random (dirichlet noise, the uniform behind choice(65, p), tie picks)."""
+
+    def __init__(self, monkeypatch):
+        self.noise, self.u_move, self.tie = [], [], []
+        real_dirichlet, real_choice = np.random.dirichlet, np.random.choice
+        tap = self
+
+        def dirichlet(alpha, size=None):
+            tap.noise.append(np.array(real_dirichlet(alpha, size), np.float64))
+            return tap.noise[-1]
+
+        def choice(a, size=None, replace=True, p=None):
+            if p is None:
+                r = real_choice(a)
+                arr = list(np.asarray(a))
+                tap.tie.append((arr.index(r), len(arr)))
+                return r
+            shadow = np.random.RandomState()
+            shadow.set_state(np.random.get_state())
+            r = real_choice(a, size, replace, p)
+            tap.u_move.append(shadow.random_sample())
+            return r
+
+        monkeypatch.setattr(np.random, "dirichlet", dirichlet)
+        monkeypatch.setattr(np.random, "choice", choice)
+
+
+class _SelfPlayStub(HashStub):
+    """HashStub with the surface one_self_play needs to rebuild a policy (self_play_worker.py:47-51)."""
+
+    def load_state_dict(self, sd):
+        pass
+
+    def eval(self):
+        pass
+
+
+SP_CASES = [  # salt, sims, c_puct, eps, alpha, temp, exploratory moves, lambda
+    (31, 12, 2.0, 0.3, 1.0, 1.0, 35, 0.98),
+    (32, 20, 1.2, 0.0, 1.0, 1.0, 6, 0.7),
+    (33, 9, 3.0, 0.5, 0.3, 1.0, 0, 1.0),
+    (34, 15, 2.0, 0.25, 1.0, 0.5, 12, 0.9),
+]
+
+
+@pytest.mark.parametrize("salt,sims,c_puct,eps,alpha,temp,nexp,lam", SP_CASES)
+def test_one_self_play_side_by_side(ref, monkeypatch, salt, sims, c_puct, eps, alpha, temp, nexp, lam):
+    """The reference's one_self_play on a fresh seed, its random draws tapped and handed to the oracle's self_play:
+    same trajectory length, canonical states, value targets (lambda-returns) bit for bit; policy targets bit for bit at
+    temperature 1 / 0 and within 1e-6 otherwise."""
+    import oracle as O
+    import self_play_worker as ref_worker
+    args = {"c_puct": c_puct, "num_simulations": sims, "num_threads": 1, "dirichlet_alpha": alpha, "dirichlet_epsilon": eps,
+            "mcts_temperature": temp, "num_exploratory_moves": nexp, "lambda": lam}
+    tap = _RngTap(monkeypatch)
+    np.random.seed(500 + salt)
+    traj = ref_worker.one_self_play((8, args, (_SelfPlayStub, {"salt": salt}, {}), None))
+    T = len(traj)
+    assert len(tap.u_move) == T and len(tap.noise) <= 1
+    # np.random.choice(best actions) is called once per temp~0 ply (MCTS_model.py:249-255), in order
+    u_tie, ties = np.zeros(128), list(tap.tie)
+    for t in range(T):
+        if (temp if t < nexp else 0.0) < 0.1:
+            k, n = ties.pop(0)
+            u_tie[t] = (k + 0.5) / n
+    assert not ties
+    u_move = np.zeros(128)
+    u_move[:T] = tap.u_move
+    stub = _SelfPlayStub(salt)
+    out = O.self_play(args, O.Evaluator(fn=stub.inference), tap.noise[0] if tap.noise else None, u_move, u_tie)
+    assert len(out["values"]) == T
+    assert np.array_equal(np.stack([t[0] for t in traj]), out["states"])
+    pis = np.stack([t[1] for t in traj])
+    if temp == 1.0:
+        assert np.array_equal(pis, out["pis"])
+    else:
+        assert np.abs(pis - out["pis"]).max() <= 1e-6
+    assert np.array_equal(np.array([t[2] for t in traj], np.float64), out["values"])
