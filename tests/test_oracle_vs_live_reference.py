@@ -234,3 +234,29 @@ def test_one_self_play_side_by_side(ref, monkeypatch, salt, sims, c_puct, eps, a
     else:
         assert np.abs(pis - out["pis"]).max() <= 1e-6
     assert np.array_equal(np.array([t[2] for t in traj], np.float64), out["values"])
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_replay_aggregation_side_by_side(ref, seed):
+    """Trainer._aggregate_duplicates (train.py:142-173, called as an unbound method on a stand-in object) against the
+    oracle restatement on fresh random buffers with heavy duplication and mixed model versions."""
+    import collections
+    import train as ref_train
+    from oracle import replay as OR
+
+    class FakeTrainer:
+        _hash_state = ref_train.Trainer._hash_state
+
+    rs = np.random.RandomState(900 + seed)
+    uniq = rs.randint(-1, 2, size=(50, 8, 8)).astype(np.int8)
+    n = 700
+    buf = [(uniq[rs.randint(0, 50)].copy(), rs.rand(65).astype(np.float32), float(rs.uniform(-1, 1)), int(rs.randint(0, 3)))
+           for _ in range(n)]
+    t = FakeTrainer()
+    t.replay_buffer = collections.deque(buf)
+    states, policies, values = ref_train.Trainer._aggregate_duplicates(t)
+    o_states, o_policies, o_values, counts, _vers = OR.aggregate_duplicates(buf)
+    assert len(states) == len(o_states) and sum(counts) == n
+    assert np.array_equal(np.stack(states), np.stack(o_states))
+    assert np.array_equal(np.stack(policies).astype(np.float32), np.stack(o_policies))
+    assert np.array_equal(np.array(values, np.float32), np.array(o_values, np.float32))
