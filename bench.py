@@ -435,6 +435,8 @@ def run_b200(a):
                                            "how": f"measured live: independent random 64-byte reads over {foot >> 20} MiB (oth_host_random_read_probe)"},
                          "move_kernel": {"kernel": "k_mcts_move (policy target, move sampling, re-rooting copy, game hand-off)",
                                          "launch_ms_avg": m_avg, "launch_ms_median": mms[len(mms) // 2], "launch_ms_max": mms[-1],
+                                         "note": "runs after every step kernel; most launches only scan the per-slot move flags "
+                                                 "(median), the copy work sits in the launch per move where the in-step games all re-root (max)",
                                          "algorithmic_bytes_per_launch": alg_move,
                                          "achieved": alg_move / (m_avg * 1e-3) / 1e9, "frac": alg_move / (m_avg * 1e-3) / 1e9 / peak},
                          "kernel_share_of_iteration": (k_avg + m_avg) / (ms / a.steps / iters)},
