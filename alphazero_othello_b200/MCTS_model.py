@@ -15,12 +15,18 @@ the GPU straight from the engine's leaf batch) or any object with
 ``policy=None`` selects the reference's rollout mode (uniform priors + one random playout per
 leaf, MCTS_model.py:276-303, 332-335) evaluated in-kernel; its playouts draw from the engine's
 Philox streams (keyed by ``seed``), not from ``np.random``.
+
+Restrictions (stated, not silent): ``args["num_threads"]`` is accepted and ignored -- searches
+run with the reference's ``num_threads=1`` semantics, the only deterministic mode (its default
+of 4 races virtual losses between Python threads); the caller's ``policy`` module is neither
+moved nor switched to eval mode, the search works on a private copy made at construction
+(later weight updates need a new ``MCTS`` object, as in the reference's workers).
 """
 import numpy as np
 import torch
 
 from . import _lib
-from .engine import MctsEngine
+from .engine import MctsEngine, private_copy
 
 
 class _Child:
@@ -62,7 +68,9 @@ class MCTS:
                              inject_random=True, device=device, max_inline_sims=64, seed=seed)
         self._module = isinstance(policy, torch.nn.Module)
         if self._module:
-            self.policy = policy.to(self.device).eval()
+            self.policy = private_copy(policy, self.device)
+        self._graph = None        # CUDA graph of (network forward + oth_mcts_step) for module policies
+        self._graph_failed = False
         self._state = None  # host copy of the root position
         self._player = None
         self.root = None
@@ -93,6 +101,52 @@ class MCTS:
         pri, val = self.policy.inference(canon, 1)  # canonical plane == player*state (Models.py:16)
         e.priors.copy_(torch.from_numpy(np.asarray(pri, np.float32)).view(1, 65))
         e.values.fill_(float(val))
+
+    def _eval_and_step(self):
+        self._evaluate()
+        self._e.step()
+
+    def _run_search(self):
+        """num_simulations simulations on the device tree.  Every launch after the first consumes one evaluation
+        and completes at least one simulation (the root initialisation excepted), so ``num_simulations + 1``
+        evaluate+launch pairs always suffice: a module policy is driven without reading anything back per
+        simulation (one CUDA-graph replay each), a host ``inference`` policy needs the leaf on the host anyway."""
+        e = self._e
+        sims = int(self.args["num_simulations"])
+        e.step()
+        if self._module:
+            if self._graph is None and not self._graph_failed:
+                self._capture()
+            for _ in range(sims + 1):
+                if self._graph is not None:
+                    self._graph.replay()
+                else:
+                    self._eval_and_step()
+        for _ in range(sims + 2):  # host policies; for module policies this loop only confirms the search is over
+            ph = int(e.ctl()["phase"][0])
+            if ph == _lib.PH_WAIT_EVAL:
+                self._evaluate()
+            elif ph != _lib.PH_RUN:
+                break
+            e.step()
+
+    def _capture(self):
+        """Capture (network forward, softmax, oth_mcts_step) once; fall back to eager launches if the module cannot
+        be captured.  The two warm-up iterations are real ones (an evaluation of a slot that is not waiting is ignored)."""
+        dev = self.device
+        try:
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s):
+                self._evaluate()  # warm-up of lazy initialisation only: outputs are rewritten by the first replay
+            torch.cuda.current_stream(dev).wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._eval_and_step()
+            self._graph = g
+        except Exception:
+            self._graph, self._graph_failed = None, True
+            torch.cuda.synchronize(dev)
 
     # -- the reference's surface -------------------------------------------------
     def make_move(self, action):
@@ -126,13 +180,7 @@ class MCTS:
             noise = np.random.dirichlet([self.dirichlet_alpha] * self.num_actions)
             e.noise[0] = torch.from_numpy(noise).to(self.device)
         e.begin_search()
-        for _ in range(self.args["num_simulations"] + 2):
-            e.step()
-            ph = int(e.ctl()["phase"][0])
-            if ph == _lib.PH_WAIT_EVAL:
-                self._evaluate()
-            elif ph != _lib.PH_RUN:
-                break
+        self._run_search()
         e.raise_on_error()
         self._refresh_root()
         counts = np.zeros(self.num_actions, dtype=np.float32)

@@ -247,19 +247,6 @@ class FoldedNet(nn.Module):
         self.n_actions = net.action_size
         self.supports_raw = True
 
-    # Experiment switch (default off -- measured: no gain, profiles/r01_l2_discard_ab.txt).  "tail": once the
-    # heads have read the trunk output, its L2 lines are dropped without write-back (oth_nn_l2_discard), the idea
-    # being that the MCTS kernel that follows would not pay a dirty-line eviction per miss; "all": additionally
-    # every residual block's dead inputs.  bf16 CUDA batches >= 1024 only.
-    l2_discard = None
-
-    def _dead(self, *tensors):
-        import ctypes as C
-        from . import _lib
-        for t in tensors:
-            _lib.check(_lib.lib().oth_nn_l2_discard(t.data_ptr(), t.numel() * t.element_size(),
-                                                    C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)))
-
     @torch.no_grad()
     def forward(self, x, raw=False):
         if x.dim() == 3:
@@ -267,25 +254,16 @@ class FoldedNet(nn.Module):
         h = self.stem(x if isinstance(self.stem, _StemGemm) else x.to(self.dtype))
         if not h.is_contiguous(memory_format=torch.channels_last):
             h = h.contiguous(memory_format=torch.channels_last)
-        mode = self.l2_discard if (h.is_cuda and self.dtype == torch.bfloat16 and h.size(0) >= 1024) else None
         for c1, c2 in self.blocks:
-            y1 = c1(h)
-            h_new = c2(y1, residual=h)
-            if mode == "all":
-                self._dead(y1, h)
-            h = h_new
+            h = c2(c1(h), residual=h)
         B = h.size(0)
         if self.kind == "small":
             t = self.tail(h)
             feat = t.permute(0, 2, 3, 1).reshape(B, -1)  # NHWC flattening: a view
-            dead = (h, t)
         else:
             hf = h.permute(0, 2, 3, 1).reshape(B * 64, -1)  # [B*64, C] view of the channels-last trunk output
             feat = torch._addmm_activation(self.heads_b, hf, self.heads_w, use_gelu=False).view(B, -1)
-            dead = (h, feat)
         y = F.linear(feat, self.head_w, self.head_b)
-        if mode:
-            self._dead(*dead)
         na, nh = self.n_actions, self.n_hidden
         v = F.linear(F.relu(y[:, na:na + nh]), self.v2_w, self.v2_b)[:, :1]
         if raw:  # engine path: (logits, value pre-activation) views in the compute dtype; softmax / tanh are

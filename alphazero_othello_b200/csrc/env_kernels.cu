@@ -364,26 +364,6 @@ extern "C" int oth_nn_bias_add_relu_bf16(void* x, const void* res, const void* b
     return cuda_status(cudaGetLastError());
 }
 
-// Dead-activation hint: drop the (dirty) L2 lines of a buffer nobody will read again, so they are neither
-// written back to HBM nor evicted -- with a write-back each -- by the next kernel's misses.
-// discard.global.L2 works on whole 128-byte lines; the range is shrunk to line boundaries.
-__global__ void __launch_bounds__(256) k_l2_discard(char* base, long n_lines)
-{
-    const long stride = (long)gridDim.x * blockDim.x;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += stride)
-        asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + i * 128) : "memory");
-}
-
-extern "C" int oth_nn_l2_discard(void* ptr, int64_t bytes, void* stream)
-{
-    if (bytes < 0 || (bytes > 0 && !ptr)) return OTH_E_ARG;
-    uintptr_t lo = ((uintptr_t)ptr + 127) & ~(uintptr_t)127, hi = ((uintptr_t)ptr + (uintptr_t)bytes) & ~(uintptr_t)127;
-    if (hi <= lo) return OTH_OK;
-    const long n_lines = (long)((hi - lo) / 128);
-    k_l2_discard<<<grid_for(n_lines, 256), 256, 0, (cudaStream_t)stream>>>((char*)lo, n_lines);
-    return cuda_status(cudaGetLastError());
-}
-
 // canonical packed boards [n][2] -> int8 [n,64] (+1 own / -1 opp)
 extern "C" int oth_unpack_canonical(const uint64_t* boards, int8_t* states, int64_t n, void* stream)
 {
@@ -523,14 +503,6 @@ extern "C" const char* oth_error_string(int code)
 
 extern "C" const char* oth_last_cuda_error(void) { return g_cuda_err; }
 
-// Device-wide hint (cudaLimitMaxL2FetchGranularity): 32 suits isolated 32-byte tree records,
-// the default 64 / 128 suits streaming kernels.  Exposed so hosts can experiment.
-extern "C" int oth_set_l2_fetch_granularity(int32_t bytes)
-{
-    if (bytes != 32 && bytes != 64 && bytes != 128) return OTH_E_ARG;
-    return cuda_status(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
-}
-
 extern "C" int oth_device_count(void)
 {
     int n = 0;
@@ -611,9 +583,14 @@ extern "C" int oth_symmetry(const int8_t* states, const float* pis, const int32_
 // ------------------------------------------------------ host-buffer forms --
 
 namespace {
-struct Scratch {  // grow-only device staging for the oth_host_* calls (not thread-safe)
+struct Scratch {  // grow-only device staging for the oth_host_* calls: one per host thread and device
     void* p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    ~Scratch()
+    {
+        for (int i = 0; i < 8; i++)
+            if (p[i]) cudaFree(p[i]);  // may run after context teardown: the error is irrelevant
+    }
     int get(int i, size_t bytes, void** out)
     {
         if (bytes > cap[i]) {
@@ -629,7 +606,17 @@ struct Scratch {  // grow-only device staging for the oth_host_* calls (not thre
         return OTH_OK;
     }
 };
-Scratch g_scr;
+// The reference's Game object is stateless and shared across the MCTS worker threads (MCTS_model.py:196-198,
+// ThreadPoolExecutor); ctypes releases the GIL during a call.  Staging buffers are therefore per calling thread and
+// per current device, so concurrent oth_host_* calls never share device memory.
+constexpr int kMaxDevices = 16;
+Scratch& scr()
+{
+    thread_local Scratch per_device[kMaxDevices];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return per_device[dev];
+}
 
 #define CK(x)                          \
     do {                               \
@@ -644,9 +631,9 @@ extern "C" int oth_host_valid_moves(const int8_t* states, const int8_t* players,
     if (n < 0 || (n > 0 && (!states || !players || !out_masks))) return OTH_E_ARG;
     if (n == 0) return OTH_OK;
     void *ds, *dp, *dm;
-    CK(g_scr.get(0, n * 64, &ds));
-    CK(g_scr.get(1, n, &dp));
-    CK(g_scr.get(2, n * 65, &dm));
+    CK(scr().get(0, n * 64, &ds));
+    CK(scr().get(1, n, &dp));
+    CK(scr().get(2, n * 65, &dm));
     CU(cudaMemcpyAsync(ds, states, n * 64, cudaMemcpyHostToDevice, 0));
     CU(cudaMemcpyAsync(dp, players, n, cudaMemcpyHostToDevice, 0));
     CK(oth_valid_moves_i8((const int8_t*)ds, (const int8_t*)dp, (uint8_t*)dm, n, 0));
@@ -661,11 +648,11 @@ extern "C" int oth_host_next_state(const int8_t* states, const int32_t* actions,
     if (n < 0 || (n > 0 && (!states || !players || !actions || !out_states || !out_flags))) return OTH_E_ARG;
     if (n == 0) return OTH_OK;
     void *ds, *dp, *da, *dout, *df;
-    CK(g_scr.get(0, n * 64, &ds));
-    CK(g_scr.get(1, n, &dp));
-    CK(g_scr.get(2, n * 4, &da));
-    CK(g_scr.get(3, n * 64, &dout));
-    CK(g_scr.get(4, n, &df));
+    CK(scr().get(0, n * 64, &ds));
+    CK(scr().get(1, n, &dp));
+    CK(scr().get(2, n * 4, &da));
+    CK(scr().get(3, n * 64, &dout));
+    CK(scr().get(4, n, &df));
     CU(cudaMemcpyAsync(ds, states, n * 64, cudaMemcpyHostToDevice, 0));
     CU(cudaMemcpyAsync(dp, players, n, cudaMemcpyHostToDevice, 0));
     CU(cudaMemcpyAsync(da, actions, n * 4, cudaMemcpyHostToDevice, 0));
@@ -686,10 +673,10 @@ extern "C" int oth_host_value_terminated(const int8_t* states, const int8_t* pla
     if (n < 0 || (n > 0 && (!states || !players || !out_values || !out_terms))) return OTH_E_ARG;
     if (n == 0) return OTH_OK;
     void *ds, *dp, *dv, *dt;
-    CK(g_scr.get(0, n * 64, &ds));
-    CK(g_scr.get(1, n, &dp));
-    CK(g_scr.get(2, n, &dv));
-    CK(g_scr.get(3, n, &dt));
+    CK(scr().get(0, n * 64, &ds));
+    CK(scr().get(1, n, &dp));
+    CK(scr().get(2, n, &dv));
+    CK(scr().get(3, n, &dt));
     CU(cudaMemcpyAsync(ds, states, n * 64, cudaMemcpyHostToDevice, 0));
     CU(cudaMemcpyAsync(dp, players, n, cudaMemcpyHostToDevice, 0));
     k_value_terminated_i8<<<grid_for(n * 32, 256), 256>>>((const int8_t*)ds, (const int8_t*)dp, (int8_t*)dv, (uint8_t*)dt, n);
@@ -706,12 +693,12 @@ extern "C" int oth_host_symmetry(const int8_t* states, const float* pis, const i
     if (n < 0 || (n > 0 && (!states || !pis || !ks || !flips_ || !out_states || !out_pis))) return OTH_E_ARG;
     if (n == 0) return OTH_OK;
     void *ds, *dpi, *dk, *df, *dos, *dop;
-    CK(g_scr.get(0, n * 64, &ds));
-    CK(g_scr.get(1, n * 65 * 4, &dpi));
-    CK(g_scr.get(2, n * 4, &dk));
-    CK(g_scr.get(3, n, &df));
-    CK(g_scr.get(4, n * 64 * 4, &dos));
-    CK(g_scr.get(5, n * 65 * 4, &dop));
+    CK(scr().get(0, n * 64, &ds));
+    CK(scr().get(1, n * 65 * 4, &dpi));
+    CK(scr().get(2, n * 4, &dk));
+    CK(scr().get(3, n, &df));
+    CK(scr().get(4, n * 64 * 4, &dos));
+    CK(scr().get(5, n * 65 * 4, &dop));
     CU(cudaMemcpyAsync(ds, states, n * 64, cudaMemcpyHostToDevice, 0));
     CU(cudaMemcpyAsync(dpi, pis, n * 65 * 4, cudaMemcpyHostToDevice, 0));
     CU(cudaMemcpyAsync(dk, ks, n * 4, cudaMemcpyHostToDevice, 0));
@@ -729,14 +716,14 @@ extern "C" int oth_host_rollout(uint64_t seed, uint64_t game_id_base, int64_t n_
 {
     if (n_games <= 0 || n_trace < 0 || n_trace > n_games) return OTH_E_ARG;
     void *dsc, *dpl, *dfin, *dta = nullptr, *dtm = nullptr, *dcnt;
-    CK(g_scr.get(0, n_games * 4, &dsc));
-    CK(g_scr.get(1, n_games * 4, &dpl));
-    CK(g_scr.get(2, n_games * 16, &dfin));
+    CK(scr().get(0, n_games * 4, &dsc));
+    CK(scr().get(1, n_games * 4, &dpl));
+    CK(scr().get(2, n_games * 16, &dfin));
     if (n_trace) {
-        CK(g_scr.get(3, n_trace * OTH_MAX_PLIES, &dta));
-        CK(g_scr.get(4, n_trace * OTH_MAX_PLIES * 8, &dtm));
+        CK(scr().get(3, n_trace * OTH_MAX_PLIES, &dta));
+        CK(scr().get(4, n_trace * OTH_MAX_PLIES * 8, &dtm));
     }
-    CK(g_scr.get(5, 64, &dcnt));
+    CK(scr().get(5, 64, &dcnt));
     CU(cudaMemsetAsync(dcnt, 0, 64, 0));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
@@ -763,7 +750,7 @@ extern "C" int oth_host_int32_peak(double* out_ips, float* kernel_ms)
 {
     const int blocks = sm_count() * 8, threads = 256, iters = 2048;
     void* d;
-    CK(g_scr.get(6, (size_t)blocks * threads * 4, &d));
+    CK(scr().get(6, (size_t)blocks * threads * 4, &d));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));

@@ -21,6 +21,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include "../../include/othello_b200.h"
@@ -34,6 +35,10 @@ using namespace oth;
 namespace {
 
 constexpr int kBlock = 128;
+#ifndef OTH_STEP_BLOCKS_PER_SM
+#define OTH_STEP_BLOCKS_PER_SM 7
+#endif
+constexpr int kStepBlocksPerSM = OTH_STEP_BLOCKS_PER_SM;  // resident step-kernel blocks per SM the register budget is sized for
 constexpr int kMoveSet = 8;  // slots per warp in k_mcts_move
 constexpr uint64_t kSaltNoise = 0x6e6f697365ULL;  // Philox purposes
 constexpr uint32_t kPurposeMove = 1, kPurposeTie = 2;
@@ -116,6 +121,8 @@ struct Params {
     unsigned* slot_counters;  // [slot][16] cumulative event counters, summed by k_mcts_poll
     uint4* hot;               // [slot] 256-byte SlotHot records
     uint8_t* move_flags;      // [slot] set by the step kernel when a slot's move is due (k_mcts_move clears it)
+    int* move_list;           // [0] slots due, [1] block tickets, [4..] due slots (cfg.move_launch = 1)
+    int hot_path;             // path entries kept in the hot record (cfg.hot_path, default kHotPath)
     const float* priors;
     const float* values;
     // fused network tail (oth_mcts_step_fused): raw logits / value pre-activations, row strides in elements
@@ -226,24 +233,30 @@ struct Ctx {
     }
     __device__ __forceinline__ void load_path_rest(int path_len)
     {
+        const int hp = P.hot_path;  // entries [0, hp) travel in the hot record, [hp, path_len) in OTH_BUF_PATH
         if (path_len > 8) {
             const uint4* g = P.hot + (size_t)slot * 16;
             uint4* d = reinterpret_cast<uint4*>(&S.hot);
-            const int n16 = 3 + (min(path_len, kHotPath) + 3) / 4;
+            const int n16 = 3 + (min(path_len, hp) + 3) / 4;
             for (int i = 5 + lane; i < n16; i += LANES) d[i] = g[i];
+        }
+        if (path_len > hp) {
             const int* gp = P.path + (size_t)slot * P.cfg.path_cap;
-            for (int k = kHotPath + lane; k < path_len; k += LANES) S.hot.path[k] = gp[k];
+            for (int k = hp + lane; k < path_len; k += LANES) S.hot.path[k] = gp[k];
         }
     }
     __device__ __forceinline__ void store_hot(int path_len)
     {
         gsync();
+        const int hp = P.hot_path;
         uint4* g = P.hot + (size_t)slot * 16;
         const uint4* d = reinterpret_cast<const uint4*>(&S.hot);
-        const int n16 = 3 + (min(path_len, kHotPath) + 3) / 4;
+        const int n16 = 3 + (min(path_len, hp) + 3) / 4;
         for (int i = lane; i < n16; i += LANES) g[i] = d[i];
-        int* gp = P.path + (size_t)slot * P.cfg.path_cap;
-        for (int k = kHotPath + lane; k < path_len; k += LANES) gp[k] = S.hot.path[k];
+        if (path_len > hp) {
+            int* gp = P.path + (size_t)slot * P.cfg.path_cap;
+            for (int k = hp + lane; k < path_len; k += LANES) gp[k] = S.hot.path[k];
+        }
     }
 
     __device__ __forceinline__ void bind_arena()
@@ -258,6 +271,24 @@ struct Ctx {
         c.error |= bit;
         c.phase = OTH_PH_ERROR;
     }
+
+    // -DOTH_DEBUG build: every arena index is checked against the slot's bump pointer / capacity before use.
+    // A violation is recorded (OTH_ERR_DEBUG, source line in ctl.reserved) and the index clamped to the root,
+    // so the launch finishes and the host can report it instead of taking an illegal-address fault.
+#ifdef OTH_DEBUG
+    __device__ __noinline__ int dbg_idx(int i, int lim, int line)
+    {
+        if ((unsigned)i >= (unsigned)lim) {
+            c.error |= OTH_ERR_DEBUG;
+            c.reserved = ((long long)line << 32) | (unsigned)i;
+            return 0;
+        }
+        return i;
+    }
+#define OTH_IDX(i, lim) dbg_idx((i), (lim), __LINE__)
+#else
+#define OTH_IDX(i, lim) (i)
+#endif
 
     // numpy pairwise add.reduce over 65 float32 in S.pri (MCTS_model.py:347, :259)
     __device__ __forceinline__ float np_sum65_f32()
@@ -409,7 +440,8 @@ struct Ctx {
             for (int e = lane; e < OTH_NUM_ACTIONS; e += LANES) {
                 double g = d;
                 for (uint32_t k = 0; k < 256; k++) {
-                    const Philox4 r = philox4x32_10(P.cfg.seed ^ kSaltNoise, (uint64_t)c.game_id, (uint32_t)e, k);
+                    // ply 0 (game start) keeps the round-1 stream; a later fresh root (manual mode) is keyed by its ply
+                    const Philox4 r = philox4x32_10(P.cfg.seed ^ kSaltNoise, (uint64_t)c.game_id, (uint32_t)e, k | ((uint32_t)c.ply << 16));
                     const double u1 = ((double)r.x + 1.0) * (1.0 / 4294967296.0);
                     const double u2 = (double)r.y * (1.0 / 4294967296.0);
                     const double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
@@ -466,6 +498,10 @@ struct Ctx {
             gsync();
             const double s = np_sum65_f64();
             gsync();
+            if (!isfinite(s)) {
+                fail(OTH_ERR_NONFINITE);
+                return false;
+            }
             if (s > 1e-12)
                 for (int a = lane; a < OTH_NUM_ACTIONS; a += LANES) S.pri64[a] = __ddiv_rn(S.pri64[a], s);
         } else {
@@ -477,6 +513,10 @@ struct Ctx {
                 gsync();
             }
             sum32 = np_sum65_f32();  // the division (priors /= sum, :348-349) is applied per child below
+            if (!isfinite(sum32)) {  // a NaN / infinite prior: stop this slot, never let it into the tree
+                fail(OTH_ERR_NONFINITE);
+                return false;
+            }
         }
         gsync();
         for (int i = lane; i < nchild; i += LANES) {
@@ -497,11 +537,11 @@ struct Ctx {
             } else {
                 ch.prior = sum32 > (float)1e-12 ? __fdiv_rn(S.pri[a], sum32) : S.pri[a];
             }
-            store_node(N + fc + i, ch);
+            store_node(N + OTH_IDX(fc + i, P.cfg.node_cap), ch);
             B[fc + i] = make_ulonglong2(cb.own, cb.opp);
         }
         if (lane == 0) {
-            Node* p = N + leaf;
+            Node* p = N + OTH_IDX(leaf, c.top);
             p->first_child = fc;
             p->meta = (lf.meta & ~0xffu) | (uint32_t)nchild;
         }
@@ -524,7 +564,7 @@ struct Ctx {
         // value): nothing is loaded, the group does not wait.  A single IEEE add per node per
         // simulation, in simulation order -> same sums as the reference's sequential loop.
         for (int d = lane; d < depth; d += LANES) {
-            Node* p = N + S.hot.path[d];
+            Node* p = N + OTH_IDX(S.hot.path[d], c.top);
             const double sv = ((depth - 1 - d) & 1) ? -value : value;
             atomicAdd(&p->N, 1);
             atomicAdd(&p->W, sv);
@@ -568,7 +608,7 @@ struct Ctx {
             if (!f64) {
                 float bs = -INFINITY;
                 for (int i = lane; i < nchild; i += LANES) {
-                    const Node ch = load_node(N + fc + i);
+                    const Node ch = load_node(N + OTH_IDX(fc + i, c.top));
                     const double q = ch.N ? -__ddiv_rn(ch.W, (double)ch.N) : -0.0;
                     float u = __fmul_rn(cp32, ch.prior);
                     u = __fmul_rn(u, sq32);
@@ -588,7 +628,7 @@ struct Ctx {
             } else {
                 double bs = -INFINITY;
                 for (int i = lane; i < nchild; i += LANES) {
-                    const Node ch = load_node(N + fc + i);
+                    const Node ch = load_node(N + OTH_IDX(fc + i, c.top));
                     const double q = ch.N ? -__ddiv_rn(ch.W, (double)ch.N) : -0.0;
                     double u = __dmul_rn(cp64, P.root_prior64[(size_t)slot * OTH_MAX_CHILDREN + i]);
                     u = __dmul_rn(u, sq);
@@ -612,6 +652,10 @@ struct Ctx {
                         bi = oi;
                     }
                 }
+            }
+            if ((unsigned)bi >= (unsigned)nchild) {  // no child compared greater than -inf: every score was NaN.  Cannot
+                fail(OTH_ERR_NONFINITE);             // happen while expansion rejects non-finite priors / values; guards
+                return -1;                           // the arena against an out-of-range child index all the same
             }
             const int src = bi & (LANES - 1);
             nd.N = gshfl(k_N, src);
@@ -669,6 +713,8 @@ struct Ctx {
     {
         Node* Ns = N;
         ulonglong2* Bs = B;
+        const int old_top = c.top;
+        (void)old_top;
         c.arena ^= 1;
         bind_arena();
         Node* Nd = N;
@@ -736,7 +782,7 @@ struct Ctx {
                             else hi = mid;
                         }
                         const int src = s_ofc[lo] + (t - s_exc[lo]);
-                        const uint4* sp = reinterpret_cast<const uint4*>(Ns + src);
+                        const uint4* sp = reinterpret_cast<const uint4*>(Ns + OTH_IDX(src, old_top));
                         x0[j] = ldcg4(sp);
                         x1[j] = ldcg4(sp + 1);
                         bb[j] = Bs[src];
@@ -746,7 +792,7 @@ struct Ctx {
 #pragma unroll
                 for (int j = 0; j < PER; j++) {
                     if (dst[j] >= 0) {
-                        uint4* d = reinterpret_cast<uint4*>(Nd + dst[j]);
+                        uint4* d = reinterpret_cast<uint4*>(Nd + OTH_IDX(dst[j], P.cfg.node_cap));
                         d[0] = x0[j];
                         d[1] = x1[j];
                         Bd[dst[j]] = bb[j];
@@ -975,7 +1021,10 @@ struct Ctx {
     //       them up in the same oth_mcts_step call with a full warp per slot.
     // STUB: device evaluators compiled in (search-only / test builds of the kernel).
     // FUSED: the network's softmax (Models.py:24-25) and tanh are applied here, on raw logits.
-    template <bool MOVE, bool STUB, bool FUSED = false>
+    // DEVSTUB: the production split (hot kernel + move kernel) with a device stub standing in for the
+    //       network: the pending leaf is evaluated by the stub when the hot kernel consumes it, so a
+    //       launch does exactly what it does behind the network -- one evaluation per slot.
+    template <bool MOVE, bool STUB, bool FUSED = false, bool DEVSTUB = false>
     __device__ void run_slot()
     {
         // (1) everything that depends only on the slot index is requested at once:
@@ -984,7 +1033,7 @@ struct Ctx {
         constexpr bool stub = STUB;
         float pv[NPL];
         float nn_value = 0.0f;
-        if (!stub && !(MOVE && !STUB)) {
+        if (!stub && !DEVSTUB && !(MOVE && !STUB)) {
             if constexpr (FUSED) {
                 if (P.raw_bf16) {
                     const __nv_bfloat16* lg = (const __nv_bfloat16*)P.logits + (size_t)slot * P.logits_stride;
@@ -1068,16 +1117,23 @@ struct Ctx {
             lf.meta = S.hot.leaf_meta;
             lf.first_child = -1;
             const ulonglong2 lb = make_ulonglong2(S.hot.leaf_own, S.hot.leaf_opp);
+            double leaf_value;
+            if constexpr (DEVSTUB) {
+                leaf_value = eval_stub(lb.x, lb.y);  // raw priors to S.pri; masked inside expand
+            } else {
 #pragma unroll
-            for (int k = 0; k < NPL; k++) {  // priors *= valid_mask (:346) fused into the staging store
-                const int a = lane + k * LANES;
-                const bool valid = a < 64 ? ((lf.moves >> a) & 1) : (lf.moves == 0);
-                if (a < OTH_NUM_ACTIONS) S.pri[a] = valid ? pv[k] : __fmul_rn(pv[k], 0.0f);
+                for (int k = 0; k < NPL; k++) {  // priors *= valid_mask (:346) fused into the staging store
+                    const int a = lane + k * LANES;
+                    const bool valid = a < 64 ? ((lf.moves >> a) & 1) : (lf.moves == 0);
+                    if (a < OTH_NUM_ACTIONS) S.pri[a] = valid ? pv[k] : __fmul_rn(pv[k], 0.0f);
+                }
+                gsync();
+                leaf_value = (double)nn_value;
             }
-            gsync();
             const bool root_init = c.flags & 1;
-            if (expand(c.pending, root_init, lf, lb, true)) {
-                backup(c.path_len, (double)nn_value);
+            if (!isfinite(leaf_value)) fail(OTH_ERR_NONFINITE);
+            else if (expand(c.pending, root_init, lf, lb, !DEVSTUB)) {
+                backup(c.path_len, leaf_value);
                 if (!root_init) {
                     c.sims_done++;
                     count(OTH_CNT_SIMS);
@@ -1102,7 +1158,10 @@ struct Ctx {
                     continue;
                 } else {
                     c.phase = OTH_PH_MOVE;  // the move kernel of this same step takes over
-                    if (lane == 0) P.move_flags[slot] = 1;
+                    if (lane == 0) {
+                        P.move_flags[slot] = 1;
+                        if (P.cfg.move_launch) P.move_list[4 + atomicAdd(P.move_list, 1)] = slot;
+                    }
                     break;
                 }
             }
@@ -1119,7 +1178,7 @@ struct Ctx {
                 continue;
             }
             const bool root_init = (depth == 1);  // the leaf is the root: policy_improve_step :234-235
-            const ulonglong2 lb = B[leaf];
+            const ulonglong2 lb = B[OTH_IDX(leaf, c.top)];
             if (root_init) {  // the mirror has no legal set: read the root record (once per game at most)
                 const Node rr = load_node(N + leaf);
                 nd.moves = rr.moves;
@@ -1142,7 +1201,7 @@ struct Ctx {
             c.path_len = depth;
             c.flags = (c.flags & ~1) | (root_init ? 1 : 0);
             c.phase = OTH_PH_WAIT_EVAL;
-            write_nn_input(lb.x, lb.y);
+            if (!DEVSTUB || P.nn_input) write_nn_input(lb.x, lb.y);
             if (lane == 0) {  // what the expansion in the next launch needs, carried in the hot record
                 S.hot.leaf_own = lb.x;
                 S.hot.leaf_opp = lb.y;
@@ -1151,6 +1210,22 @@ struct Ctx {
             }
         }
         count_max(OTH_CNT_MAX_TOP, (unsigned)c.top);  // arena high-water mark of this slot
+#ifdef OTH_DEBUG
+        {  // an assertion may have fired on any lane: lane 0 writes the control block
+            int e = c.error;
+            long long r = (c.error & OTH_ERR_DEBUG) ? c.reserved : -1;
+#pragma unroll
+            for (int o = LANES / 2; o; o >>= 1) {
+                e |= gshfl_xor(e, o);
+                r = max(r, gshfl_xor(r, o));
+            }
+            if (e & OTH_ERR_DEBUG) {
+                c.error = e;
+                c.reserved = r;
+                c.phase = OTH_PH_ERROR;
+            }
+        }
+#endif
         if (lane == 0) P.ctl[slot] = c;
         store_hot(c.phase == OTH_PH_WAIT_EVAL ? c.path_len : 0);
         store_counters();
@@ -1158,9 +1233,39 @@ struct Ctx {
     }
 };
 
+__global__ void k_mcts_move_list(const Params P, const int n_due);
+
+// cfg.move_launch = 1: the last block of a step kernel to finish launches the move kernel from the device, after
+// the step grid (cudaStreamTailLaunch), and only if some slot's move is due -- one warp per due slot, no flag scan,
+// nothing at all in the common launch where no slot moves.  Stream order is kept: the step grid is not complete
+// for the next kernel in the stream until its tail launch has completed.
+__device__ __noinline__ void launch_move_from_device(const Params& P, int n)
+{
+    const int blocks = (n + kBlock / 32 - 1) / (kBlock / 32);
+    k_mcts_move_list<<<blocks, kBlock, 0, cudaStreamTailLaunch>>>(P, n);
+}
+
+__device__ __forceinline__ void step_tail(const Params& P)
+{
+#ifndef OTH_NO_TAIL
+    if (!P.cfg.move_launch) return;
+    __syncthreads();  // every group of this block has appended its due slot
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int t = atomicAdd(P.move_list + 1, 1);
+        if (t == (int)gridDim.x - 1) {
+            __threadfence();
+            const int n = atomicExch(P.move_list, 0);
+            P.move_list[1] = 0;
+            if (n > 0) launch_move_from_device(P, n);
+        }
+    }
+#endif
+}
+
 // The hot kernel (external network): expansion, backup, descent.  Moves are only flagged.
 template <int LANES>
-__global__ void __launch_bounds__(kBlock, 8) k_mcts_step(const Params P)
+__global__ void __launch_bounds__(kBlock, kStepBlocksPerSM) k_mcts_step(const Params P)
 {
     __shared__ Scratch scratch[kBlock / LANES];
     cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
@@ -1170,11 +1275,28 @@ __global__ void __launch_bounds__(kBlock, 8) k_mcts_step(const Params P)
         ctx.slot = s;
         ctx.template run_slot<false, false>();
     }
+    step_tail(P);
+}
+
+// The hot kernel with a device stub in the network's place (cfg.split_stub): search-only runs and parity tests of
+// the production kernel pair at sizes where recording a real network's outputs is impractical.
+template <int LANES>
+__global__ void __launch_bounds__(kBlock, kStepBlocksPerSM) k_mcts_step_devstub(const Params P)
+{
+    __shared__ Scratch scratch[kBlock / LANES];
+    cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
+    Ctx<LANES> ctx(tile, P, scratch[threadIdx.x / LANES]);
+    const int groups = (gridDim.x * kBlock) / LANES;
+    for (int s = (blockIdx.x * kBlock + threadIdx.x) / LANES; s < P.cfg.n_slots; s += groups) {
+        ctx.slot = s;
+        ctx.template run_slot<false, false, false, true>();
+    }
+    step_tail(P);
 }
 
 // The hot kernel with the network's softmax / tanh fused in (oth_mcts_step_fused).
 template <int LANES>
-__global__ void __launch_bounds__(kBlock, 8) k_mcts_step_fused(const Params P)
+__global__ void __launch_bounds__(kBlock, kStepBlocksPerSM) k_mcts_step_fused(const Params P)
 {
     __shared__ Scratch scratch[kBlock / LANES];
     cg::thread_block_tile<LANES> tile = cg::tiled_partition<LANES>(cg::this_thread_block());
@@ -1184,6 +1306,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_mcts_step_fused(const Params P)
         ctx.slot = s;
         ctx.template run_slot<false, false, true>();
     }
+    step_tail(P);
 }
 
 // Device-evaluator build (stubs / rollouts): everything in one kernel, whole simulations per launch.
@@ -1224,6 +1347,22 @@ __global__ void __launch_bounds__(kBlock) k_mcts_move(const Params P)
             if (lane == 0) P.move_flags[ctx.slot] = 0;
             __syncwarp();
         }
+    }
+}
+
+// The move kernel as launched from the device (step_tail): one warp per due slot, slots taken from the list
+// the step kernel wrote.
+__global__ void __launch_bounds__(kBlock) k_mcts_move_list(const Params P, const int n_due)
+{
+    __shared__ Scratch scratch[kBlock / 32];
+    cg::thread_block_tile<32> tile = cg::tiled_partition<32>(cg::this_thread_block());
+    Ctx<32> ctx(tile, P, scratch[threadIdx.x / 32]);
+    const int warps = (gridDim.x * kBlock) / 32;
+    for (int w = (blockIdx.x * kBlock + threadIdx.x) / 32; w < n_due; w += warps) {
+        ctx.slot = P.move_list[4 + w];
+        ctx.template run_slot<true, false>();
+        if ((threadIdx.x & 31) == 0) P.move_flags[ctx.slot] = 0;
+        __syncwarp();
     }
 }
 
@@ -1351,6 +1490,8 @@ __global__ void __launch_bounds__(kBlock) k_mcts_advance(const Params P, const i
             ctx.c.player = -ctx.c.player;
             ctx.c.sims_done = 0;
             ctx.c.phase = OTH_PH_IDLE;
+            // a search that starts on an unexpanded root draws fresh Dirichlet noise (MCTS_model.py:234-235, 339-343)
+            if (ctx.S.hot.root_fc < 0 && P.cfg.dirichlet_epsilon > 0.0) ctx.make_noise();
         }
         if (ctx.lane == 0) P.ctl[s] = ctx.c;
         ctx.store_hot(0);
@@ -1406,7 +1547,9 @@ int check_cfg(const oth_mcts_config* cfg)
     if (cfg->num_simulations < 0 || cfg->max_inline_sims <= 0) return OTH_E_ARG;
     if (cfg->lanes != 8 && cfg->lanes != 16 && cfg->lanes != 32) return OTH_E_ARG;
     if (cfg->eval_kind < OTH_EVAL_EXTERNAL || cfg->eval_kind > OTH_EVAL_ROLLOUT) return OTH_E_ARG;
-    if (cfg->fused_softmax) return OTH_E_ARG;  // reserved
+    if (cfg->hot_path < 0 || cfg->hot_path > kHotPath) return OTH_E_ARG;
+    if (cfg->split_stub && (cfg->eval_kind < OTH_EVAL_STUB_A || cfg->eval_kind > OTH_EVAL_STUB_H)) return OTH_E_ARG;
+    if (cfg->move_launch != 0 && cfg->move_launch != 1) return OTH_E_ARG;
     if (cfg->self_play && (cfg->out_pos_cap <= 0 || cfg->out_game_cap <= 0)) return OTH_E_ARG;
     return OTH_OK;
 }
@@ -1443,6 +1586,8 @@ int make_params(const oth_mcts_config* cfg, const oth_mcts_buffers* b, Params* p
     p->slot_counters = (unsigned*)b->buf[OTH_BUF_SLOT_COUNTERS];
     p->hot = (uint4*)b->buf[OTH_BUF_HOT];
     p->move_flags = (uint8_t*)b->buf[OTH_BUF_MOVE_FLAGS];
+    p->move_list = (int*)b->buf[OTH_BUF_MOVE_LIST];
+    p->hot_path = cfg->hot_path > 0 ? cfg->hot_path : kHotPath;
     p->priors = nullptr;
     p->values = nullptr;
     p->logits = nullptr;
@@ -1508,6 +1653,7 @@ extern "C" int oth_mcts_buffer_bytes(const oth_mcts_config* cfg, int64_t* out)
     out[OTH_BUF_SLOT_COUNTERS] = G * CNT_LOCAL * 4;
     out[OTH_BUF_HOT] = G * 256;
     out[OTH_BUF_MOVE_FLAGS] = ((G + 63) / 64) * 64;
+    out[OTH_BUF_MOVE_LIST] = (4 + G) * 4;
     return OTH_OK;
 }
 
@@ -1517,6 +1663,8 @@ extern "C" int oth_mcts_reset(const oth_mcts_config* cfg, const oth_mcts_buffers
     const int rc = make_params(cfg, b, &p);
     if (rc != OTH_OK) return rc;
     int e = cuda_status(cudaMemsetAsync(p.counters, 0, 16 * 8, (cudaStream_t)stream));
+    if (e != OTH_OK) return e;
+    e = cuda_status(cudaMemsetAsync(p.move_list, 0, 16, (cudaStream_t)stream));
     if (e != OTH_OK) return e;
     LAUNCH_LANES(k_mcts_reset, mcts_grid(cfg), stream, p);
     return cuda_status(cudaGetLastError());
@@ -1553,61 +1701,77 @@ extern "C" int oth_mcts_begin_search(const oth_mcts_config* cfg, const oth_mcts_
     return oth_mcts_begin_search_masked(cfg, b, nullptr, stream);
 }
 
-// ---- per-launch kernel timing (oth_mcts_profile_begin / _end): CUDA events recorded on the launching stream
-// around the step kernel and around the move kernel, so a bench can time each of them inside its pipeline.
+// ---- per-launch kernel timing (othello_b200_experimental.h): CUDA events recorded on the launching stream around
+// the step kernel and around the move kernel.  The state lives in a handle the caller attaches to its
+// oth_mcts_buffers -- one per engine, nothing global.
 namespace {
 struct LaunchProfile {
     cudaEvent_t* ev = nullptr;  // 3 per launch: before step, after step, after move
     int cap = 0, n = 0;
-    bool on = false;
-} g_prof;
+};
 
-inline bool prof_mark(int which, void* stream)
+inline bool prof_mark(const oth_mcts_buffers* b, int which, void* stream)
 {
-    if (!g_prof.on || g_prof.n >= g_prof.cap) return false;
-    cudaEventRecord(g_prof.ev[3 * g_prof.n + which], (cudaStream_t)stream);
+    LaunchProfile* pr = (LaunchProfile*)b->profile;
+    if (!pr || pr->n >= pr->cap) return false;
+    cudaEventRecord(pr->ev[3 * pr->n + which], (cudaStream_t)stream);
     return true;
 }
+inline void prof_next(const oth_mcts_buffers* b) { ((LaunchProfile*)b->profile)->n++; }
 }  // namespace
 
-extern "C" int oth_mcts_profile_begin(int32_t max_launches)
+extern "C" int oth_mcts_profile_create(int32_t max_launches, void** out_handle)
 {
-    if (max_launches <= 0 || max_launches > (1 << 20)) return OTH_E_ARG;
-    if (g_prof.ev) {
-        for (int i = 0; i < 3 * g_prof.cap; i++) cudaEventDestroy(g_prof.ev[i]);
-        delete[] g_prof.ev;
-        g_prof.ev = nullptr;
-    }
-    g_prof.ev = new cudaEvent_t[3 * (size_t)max_launches];
+    if (max_launches <= 0 || max_launches > (1 << 20) || !out_handle) return OTH_E_ARG;
+    LaunchProfile* pr = new LaunchProfile;
+    pr->ev = new cudaEvent_t[3 * (size_t)max_launches];
     for (int i = 0; i < 3 * max_launches; i++)
-        if (cudaEventCreate(&g_prof.ev[i]) != cudaSuccess) return cuda_status(cudaGetLastError());
-    g_prof.cap = max_launches;
-    g_prof.n = 0;
-    g_prof.on = true;
+        if (cudaEventCreate(&pr->ev[i]) != cudaSuccess) {
+            for (int k = 0; k < i; k++) cudaEventDestroy(pr->ev[k]);
+            delete[] pr->ev;
+            delete pr;
+            return cuda_status(cudaGetLastError());
+        }
+    pr->cap = max_launches;
+    *out_handle = pr;
     return OTH_OK;
 }
 
-extern "C" int oth_mcts_profile_end(float* step_ms, float* move_ms, int32_t* n_launches)
+extern "C" int oth_mcts_profile_read(void* handle, float* step_ms, float* move_ms, int32_t* n_launches)
 {
-    if (!g_prof.ev || !n_launches) return OTH_E_ARG;
-    g_prof.on = false;
-    const int n = g_prof.n;
+    LaunchProfile* pr = (LaunchProfile*)handle;
+    if (!pr || !n_launches) return OTH_E_ARG;
+    const int n = pr->n;
     int rc = OTH_OK;
     for (int i = 0; i < n && rc == OTH_OK; i++) {
-        if (cudaEventSynchronize(g_prof.ev[3 * i + 2]) != cudaSuccess) rc = cuda_status(cudaGetLastError());
+        if (cudaEventSynchronize(pr->ev[3 * i + 2]) != cudaSuccess) rc = cuda_status(cudaGetLastError());
         float a = 0.f, c = 0.f;
-        if (rc == OTH_OK && (cudaEventElapsedTime(&a, g_prof.ev[3 * i], g_prof.ev[3 * i + 1]) != cudaSuccess ||
-                             cudaEventElapsedTime(&c, g_prof.ev[3 * i + 1], g_prof.ev[3 * i + 2]) != cudaSuccess))
+        if (rc == OTH_OK && (cudaEventElapsedTime(&a, pr->ev[3 * i], pr->ev[3 * i + 1]) != cudaSuccess ||
+                             cudaEventElapsedTime(&c, pr->ev[3 * i + 1], pr->ev[3 * i + 2]) != cudaSuccess))
             rc = cuda_status(cudaGetLastError());
         if (step_ms) step_ms[i] = a;
         if (move_ms) move_ms[i] = c;
     }
     *n_launches = n;
-    for (int i = 0; i < 3 * g_prof.cap; i++) cudaEventDestroy(g_prof.ev[i]);
-    delete[] g_prof.ev;
-    g_prof.ev = nullptr;
-    g_prof.cap = g_prof.n = 0;
+    pr->n = 0;
     return rc;
+}
+
+extern "C" int oth_mcts_profile_destroy(void* handle)
+{
+    LaunchProfile* pr = (LaunchProfile*)handle;
+    if (!pr) return OTH_E_ARG;
+    for (int i = 0; i < 3 * pr->cap; i++) cudaEventDestroy(pr->ev[i]);
+    delete[] pr->ev;
+    delete pr;
+    return OTH_OK;
+}
+
+// The move kernel after a step kernel: host-launched flag scan (move_launch = 0) or nothing here (the step
+// kernel's last block tail-launches k_mcts_move_list when a move is due).
+static inline void launch_move(const oth_mcts_config* cfg, const Params& p, void* stream)
+{
+    if (cfg->self_play && !cfg->move_launch) k_mcts_move<<<move_grid(cfg), kBlock, 0, (cudaStream_t)stream>>>(p);
 }
 
 extern "C" int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const float* priors, const float* values,
@@ -1620,21 +1784,22 @@ extern "C" int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers*
     p.priors = priors;
     p.values = values;
     p.nn_input = nn_input;
-    const bool prof = prof_mark(0, stream);
-    if (cfg->eval_kind != OTH_EVAL_EXTERNAL) {
+    nvtxRangePushA("oth_mcts_step");
+    const bool prof = prof_mark(b, 0, stream);
+    if (cfg->eval_kind != OTH_EVAL_EXTERNAL && !cfg->split_stub) {
         LAUNCH_LANES(k_mcts_step_stub, mcts_grid(cfg), stream, p);
-        if (prof) prof_mark(1, stream);
+        if (prof) prof_mark(b, 1, stream);
     } else {
-        LAUNCH_LANES(k_mcts_step, mcts_grid(cfg), stream, p);
-        if (prof) prof_mark(1, stream);
-        if (cfg->self_play) {
-            k_mcts_move<<<move_grid(cfg), kBlock, 0, (cudaStream_t)stream>>>(p);
-        }
+        if (cfg->eval_kind != OTH_EVAL_EXTERNAL) LAUNCH_LANES(k_mcts_step_devstub, mcts_grid(cfg), stream, p);
+        else LAUNCH_LANES(k_mcts_step, mcts_grid(cfg), stream, p);
+        if (prof) prof_mark(b, 1, stream);
+        launch_move(cfg, p, stream);
     }
     if (prof) {
-        prof_mark(2, stream);
-        g_prof.n++;
+        prof_mark(b, 2, stream);
+        prof_next(b);
     }
+    nvtxRangePop();
     return cuda_status(cudaGetLastError());
 }
 
@@ -1656,16 +1821,16 @@ extern "C" int oth_mcts_step_fused(const oth_mcts_config* cfg, const oth_mcts_bu
     p.priors_out = priors_out;
     p.values_out = values_out;
     p.nn_input = nn_input;
-    const bool prof = prof_mark(0, stream);
+    nvtxRangePushA("oth_mcts_step_fused");
+    const bool prof = prof_mark(b, 0, stream);
     LAUNCH_LANES(k_mcts_step_fused, mcts_grid(cfg), stream, p);
-    if (prof) prof_mark(1, stream);
-    if (cfg->self_play) {
-        k_mcts_move<<<move_grid(cfg), kBlock, 0, (cudaStream_t)stream>>>(p);
-    }
+    if (prof) prof_mark(b, 1, stream);
+    launch_move(cfg, p, stream);
     if (prof) {
-        prof_mark(2, stream);
-        g_prof.n++;
+        prof_mark(b, 2, stream);
+        prof_next(b);
     }
+    nvtxRangePop();
     return cuda_status(cudaGetLastError());
 }
 

@@ -5,12 +5,21 @@ network only; every search / env / self-play step is a kernel behind the C ABI
 (include/othello_b200.h).  One process drives one GPU; games are sharded over
 ranks by game id (no collective on the search path).
 """
+import copy
 import ctypes as C
+import os
 
 import numpy as np
 import torch
 
 from . import _lib
+
+
+def default_lanes(n_slots):
+    """Threads per slot.  A slot's work per launch is one dependent chain (expand, back up, descend); 32 lanes keep
+    every step of it one round wide (<= 32 children) and free of intra-warp divergence between slots.  8 lanes -- four
+    slots per warp -- only pay once 32 lanes would need more than one wave of the 7 x 148 resident 128-thread blocks."""
+    return 32 if n_slots * 32 <= 7 * 148 * 128 else (16 if n_slots * 16 <= 7 * 148 * 128 else 8)
 
 
 def default_node_cap(num_simulations):
@@ -28,8 +37,9 @@ class MctsEngine:
     """
 
     def __init__(self, n_slots, args, *, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=-1,
-                 device="cuda:0", node_cap=None, path_cap=128, max_inline_sims=8, inject_random=False, lanes=8,
-                 seed=0, game_id_base=0, game_id_stride=None, stub_salt=0, out_pos_cap=None, out_game_cap=None):
+                 device="cuda:0", node_cap=None, path_cap=128, max_inline_sims=8, inject_random=False, lanes=None,
+                 seed=0, game_id_base=0, game_id_stride=None, stub_salt=0, out_pos_cap=None, out_game_cap=None,
+                 hot_path=0, split_stub=False, move_launch=None):
         _lib.require_device()
         self.device = torch.device(device)
         self.n_slots = int(n_slots)
@@ -44,8 +54,12 @@ class MctsEngine:
         cfg.games_per_slot = int(games_per_slot)
         cfg.max_inline_sims = int(max_inline_sims)
         cfg.inject_random = 1 if inject_random else 0
-        cfg.fused_softmax = 0
-        cfg.lanes = int(lanes)
+        cfg.lanes = int(lanes or default_lanes(self.n_slots))
+        cfg.hot_path = int(hot_path)
+        cfg.split_stub = 1 if split_stub else 0
+        if move_launch is None:
+            move_launch = int(os.environ.get("OTH_MOVE_LAUNCH", "1"))
+        cfg.move_launch = int(move_launch)
         if out_game_cap is None:
             out_game_cap = self.n_slots * (2 if games_per_slot < 0 else max(1, games_per_slot)) + 16
         if out_pos_cap is None:
@@ -151,6 +165,24 @@ class MctsEngine:
                    self.values.data_ptr() if record else None, self.nn_input.data_ptr(), self._stream())
         self.launches += 1
 
+    # per-launch timing of the step / move kernels (othello_b200_experimental.h), per engine
+    def profile_begin(self, max_launches):
+        h = C.c_void_p()
+        _lib.check(self.L.oth_mcts_profile_create(int(max_launches), C.byref(h)), "oth_mcts_profile_create")
+        self.bufs.profile = h.value
+        self._prof_cap = int(max_launches)
+
+    def profile_end(self):
+        """-> (step_ms list, move_ms list) of the launches recorded since profile_begin; detaches the handle."""
+        h, cap = self.bufs.profile, self._prof_cap
+        self.bufs.profile = None
+        a, b, n = (C.c_float * cap)(), (C.c_float * cap)(), C.c_int32(0)
+        try:
+            _lib.check(self.L.oth_mcts_profile_read(h, a, b, C.byref(n)), "oth_mcts_profile_read")
+        finally:
+            self.L.oth_mcts_profile_destroy(h)
+        return list(a[: n.value]), list(b[: n.value])
+
     def advance(self, actions):
         self._call(self.L.oth_mcts_advance, actions.data_ptr(), self._stream())
 
@@ -182,6 +214,7 @@ class MctsEngine:
         """Collect the replay tuples of games finished since the last drain and reset the
         output ring.  Returns dict(boards int64[n,2] (own,opp canonical), pis f32[n,65],
         values f64[n], meta int64[n], games int64[g,4] = (game_id, first, n, winner))."""
+        torch.cuda.nvtx.range_push("oth:drain")
         cnt = self.counters_t[_lib.CNT_POSITIONS:_lib.CNT_OUT_GAMES + 1].cpu()
         n, g = int(cnt[0]), int(cnt[1])
         n, g = min(n, self.cfg.out_pos_cap), min(g, self.cfg.out_game_cap)
@@ -202,7 +235,17 @@ class MctsEngine:
         else:
             out = {k: v.clone() for k, v in out.items()}
         self.counters_t[_lib.CNT_POSITIONS:_lib.CNT_OUT_GAMES + 1].zero_()
+        torch.cuda.nvtx.range_pop()
         return out
+
+
+def private_copy(policy, device):
+    """The caller's module is never moved or switched to eval mode: like the reference's workers, which rebuild the
+    network from (class, config, state_dict) (self_play_worker.py:49-52), the engine works on its own copy."""
+    on_dev = next((p.device for p in policy.parameters()), None) == torch.device(device)
+    if on_dev and not policy.training:
+        return policy  # already an inference copy on the right device (e.g. a FoldedNet the caller built)
+    return copy.deepcopy(policy).to(device).eval()
 
 
 class BatchedPolicy:
@@ -214,7 +257,7 @@ class BatchedPolicy:
     def __init__(self, policy, device="cuda:0", dtype=torch.float32):
         self.device = torch.device(device)
         self.dtype = dtype
-        self.policy = policy.to(self.device).eval()
+        self.policy = private_copy(policy, self.device)
         if dtype != torch.float32:
             self.policy = self.policy.to(memory_format=torch.channels_last)
 
@@ -250,8 +293,11 @@ class SelfPlayRunner:
     """Batched replacement of ``Trainer.collect_self_play_games`` (train.py:199-225):
     plays ``n_slots`` concurrent games with one network evaluation per simulation per game."""
 
-    def __init__(self, engine, evaluator=None, use_graph=True, fused=True):
+    def __init__(self, engine, evaluator=None, use_graph=True, fused=True, record=False):
+        """``record=True``: every launch also writes the priors / values it consumed to ``engine.priors`` /
+        ``engine.values`` (fused path: what the kernel's own softmax / tanh produced), so a checker can replay them."""
         self.e = engine
+        self.record = record
         self.evaluator = evaluator
         self.external = engine.cfg.eval_kind == _lib.EVAL_EXTERNAL
         assert not self.external or evaluator is not None
@@ -263,7 +309,7 @@ class SelfPlayRunner:
     def _iteration(self):
         if self.external and self.fused:
             logits, v = self.evaluator.raw(self.e.nn_input)
-            self.e.step_fused(logits, v)
+            self.e.step_fused(logits, v, record=self.record)
             return
         if self.external:
             self.evaluator(self.e.nn_input, self.e.priors, self.e.values)
@@ -271,6 +317,9 @@ class SelfPlayRunner:
 
     def warm_start(self):
         self.e.reset()
+        if self.external:
+            self.e.priors.fill_(1.0 / 65.0)  # nothing is consumed by the first launch, but keep the operands finite
+            self.e.values.zero_()
         self.e.step()  # emits the root leaves
 
     def _capture(self):
@@ -290,12 +339,14 @@ class SelfPlayRunner:
         """n x (network forward over the leaf batch + one fused MCTS kernel launch), as CUDA-graph replays."""
         if self.use_graph and self.graph is None:
             self._capture()
+        torch.cuda.nvtx.range_push(f"selfplay:{n} iterations (network + oth_mcts_step)")
         for _ in range(n):
             if self.graph is not None:
                 self.graph.replay()
                 self.e.launches += 1
             else:
                 self._iteration()
+        torch.cuda.nvtx.range_pop()
 
     def play(self, check_every=64, max_iterations=None):
         """Run until every slot is DONE; returns the drained replay tuples."""

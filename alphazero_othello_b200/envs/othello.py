@@ -9,6 +9,7 @@ tensors of packed bitboards, which is what the self-play engine uses.
 There is no CPU implementation in this package.
 """
 import ctypes as C
+import sys
 
 import numpy as np
 
@@ -141,6 +142,13 @@ def symmetry_batch(states, pis, ks, flips):
 def get_random_symmetry(state, pi):
     """Drop-in for envs/othello.py:501-526: same np.random draws (randint(4), then
     rand() < 0.5), same output shapes/dtypes ((1, n, n) float32, (n*n+1,) float32)."""
+    tud = sys.modules.get("torch.utils.data")
+    if tud is not None and tud.get_worker_info() is not None:
+        # train.py:26-42 calls this per sample inside DataLoader workers (forked children of a process that already
+        # holds a CUDA context): CUDA cannot be used there.  Augment the collated batch in the training process
+        # instead -- replay.augment_batch / BatchedOthello.random_symmetry (INTEGRATION.md section 2).
+        raise RuntimeError("get_random_symmetry runs on the GPU and cannot be called from a DataLoader worker; "
+                           "use alphazero_othello_b200.replay.augment_batch on the collated batch")
     k = np.random.randint(4)
     flip = np.random.rand() < 0.5
     state = np.asarray(state)

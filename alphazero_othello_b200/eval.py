@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import MctsEngine
+from .engine import MctsEngine, private_copy
 from .envs.othello import OthelloGameNew
 
 
@@ -24,15 +24,27 @@ def _pack(states, players):
     return own.view(np.int64), opp.view(np.int64)
 
 
+class DeviceStubPolicy:
+    """A deterministic evaluator that lives in the kernels (OTH_EVAL_STUB_A / _B / _H of the C ABI) in the place of a
+    network: parity tests replay matches of the reference played with the same stub, benches search without a network."""
+
+    KINDS = {"A": _lib.EVAL_STUB_A, "B": _lib.EVAL_STUB_B, "H": _lib.EVAL_STUB_H}
+
+    def __init__(self, kind="H", salt=0):
+        self.eval_kind, self.salt = self.KINDS[kind], int(salt)
+
+
 class _Side:
     """One network + one manual-mode engine holding a tree per match."""
 
     def __init__(self, policy, args, n, device, lanes, dtype):
         from .Models import fold_for_inference
-        self.eng = MctsEngine(n, args, self_play=False, eval_kind=_lib.EVAL_EXTERNAL, device=device, lanes=lanes,
-                              max_inline_sims=16)
-        net = policy.to(device).eval()
-        self.net = fold_for_inference(net, dtype) if dtype is not None else net
+        self.stub = isinstance(policy, DeviceStubPolicy)
+        self.eng = MctsEngine(n, args, self_play=False, eval_kind=policy.eval_kind if self.stub else _lib.EVAL_EXTERNAL,
+                              stub_salt=policy.salt if self.stub else 0, device=device, lanes=lanes, max_inline_sims=16)
+        if not self.stub:
+            net = private_copy(policy, device)
+            self.net = fold_for_inference(net, dtype) if dtype is not None else net
         self.has_tree = np.zeros(n, bool)  # "self.root is None" of the reference until the first own search
         self.record = None
 
@@ -56,18 +68,21 @@ class _Side:
         e.begin_search(mask)
         e.step()
         for _ in range(sims + 1):
-            self.evaluate()
-            if self.record is not None:
-                self.record(self)  # test hook: sees (nn_input, priors, values, phases) of this evaluation
+            if not self.stub:
+                self.evaluate()
+                if self.record is not None:
+                    self.record(self)  # test hook: sees (nn_input, priors, values, phases) of this evaluation
             e.step()
         assert e.counters()["active"] == 0, "search did not finish"
 
 
-def play_matches_batched(policy_a, policy_b, args, n_matches, *, device="cuda:0", lanes=8, dtype=torch.bfloat16, record=None,
-                         max_plies=128):
+def play_matches_batched(policy_a, policy_b, args, n_matches, *, device="cuda:0", lanes=None, dtype=torch.bfloat16, record=None,
+                         max_plies=128, u_tie=None):
     """n_matches concurrent games; match i: policy_a plays +1 if i is even, policy_b otherwise
     (eval.py:115-126).  Returns (results, log): results[i] in {"A", "B", "Draw"} from policy_a's
-    point of view as evaluate_models_parallel counts them; log holds per-match actions and tie uniforms."""
+    point of view as evaluate_models_parallel counts them; log holds per-match actions and tie uniforms.
+    ``u_tie`` float64 [n_matches, max_plies]: the tie-pick uniforms to use instead of drawing them (replay of a
+    logged match, or of a match of the reference whose np.random.choice(best_actions) picks were tapped)."""
     env = OthelloGameNew(8)
     n = int(n_matches)
     sims = int(args["num_simulations"])
@@ -95,7 +110,7 @@ def play_matches_batched(policy_a, policy_b, args, n_matches, *, device="cuda:0"
         for i in np.nonzero(active)[0]:
             counts = (ca if a_moves[i] else cb)[i].astype(np.float32)
             best = np.where(counts == counts.max())[0]  # MCTS_model.py:249-255, then np.argmax (eval.py:161)
-            u = np.random.random_sample()
+            u = np.random.random_sample() if u_tie is None else float(u_tie[i, ply])
             actions[i] = best[min(int(u * len(best)), len(best) - 1)]
             log["u_tie"][i, ply] = u
             log["actions"][i, ply] = actions[i]

@@ -56,6 +56,24 @@ def to_training_arrays(agg):
     return states.float(), agg["pis"], agg["values"].reshape(-1, 1)
 
 
+def augment_batch(states, policies, device="cuda:0", generator=None):
+    """Training-time augmentation of a COLLATED batch in the training process -- the replacement of the
+    per-sample ``get_random_symmetry`` call in ``RandomSymmetryDataset.__getitem__`` (train.py:26-42), which
+    the reference runs inside forked DataLoader workers where CUDA cannot be used.  The dataset yields the raw
+    ``(state [8,8], policy [65], value)`` rows (any worker count); the training loop calls this on each batch:
+
+        for state, pi, v in dataloader:                       # raw rows, workers never touch CUDA
+            state, pi = augment_batch(state, pi, device)      # one random dihedral image per sample, on the GPU
+
+    states: [B,8,8] or [B,1,8,8] (any real dtype, values in {-1,0,1}); policies: float [B,65].
+    Returns (float32 [B,1,8,8], float32 [B,65]) on ``device`` -- the shapes/dtypes the per-sample path collates to."""
+    from .envs.othello import BatchedOthello
+    dev = torch.device(device)
+    st = states.to(dev).reshape(-1, 8, 8).to(torch.int8).contiguous()
+    pi = policies.to(dev, torch.float32).contiguous()
+    return BatchedOthello(dev).random_symmetry(st, pi, generator=generator)
+
+
 def pack_states(states):
     """int8 canonical boards [n,8,8] (numpy) -> int64[n,2] (own, opp), bit i = row*8+col."""
     s = np.asarray(states).reshape(len(states), 64)

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from .MCTS_model import MCTS
-from .engine import BatchedPolicy, MctsEngine, SelfPlayRunner, split_games
+from .engine import BatchedPolicy, MctsEngine, SelfPlayRunner, private_copy, split_games
 from .envs.othello import OthelloGameNew as OthelloGame
 
 
@@ -82,7 +82,7 @@ def collect_self_play_games(policy, args, n_games, *, n_slots=None, device="cuda
     gps = -(-n_games // n_slots)
     eng = MctsEngine(n_slots, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=gps, device=device,
                      seed=seed, game_id_base=game_id_base)
-    net = policy.to(device).eval()
+    net = private_copy(policy, device)  # the trainer's module stays where it is, in the mode it is in
     if fold:
         net = fold_for_inference(net, dtype)
         ev = BatchedPolicy(net, device, torch.float32)
@@ -103,7 +103,7 @@ def collect_self_play_games_distributed(policy, args, n_games_per_rank, *, n_slo
     from .Models import fold_for_inference
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cuda", torch.cuda.current_device())
-    net = policy.to(dev).eval()
+    net = private_copy(policy, dev)
     parallel.broadcast_weights(net, src=0, version=version)
     n_slots = int(n_slots or min(n_games_per_rank, 4096))
     gps = -(-n_games_per_rank // n_slots)

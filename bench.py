@@ -203,18 +203,12 @@ def run_b200(a):
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
-    if os.environ.get("OTH_L2_FETCH"):  # experiment: cudaLimitMaxL2FetchGranularity (0x05) = 32 / 64 / 128
-        rc = _lib.lib().oth_set_l2_fetch_granularity(int(os.environ["OTH_L2_FETCH"]))
-        print("cudaDeviceSetLimit(L2 fetch granularity)", os.environ["OTH_L2_FETCH"], "->", rc, file=sys.stderr)
     desc, kind, G, sims = WORKLOADS[a.workload]
     if a.games:
         G = a.games
     iters = a.iters_per_step or sims
     args = dict(TRAIN_ARGS, num_simulations=sims)
 
-    if os.environ.get("OTH_L2_DISCARD"):  # A/B: off | tail | all
-        from alphazero_othello_b200 import Models
-        Models.FoldedNet.l2_discard = {"off": None}.get(os.environ["OTH_L2_DISCARD"], os.environ["OTH_L2_DISCARD"])
     if os.environ.get("OTH_NO_GRAPH_FUSION"):
         from alphazero_othello_b200 import Models
         Models._FusedConv.graph_fusion = False
@@ -241,8 +235,10 @@ def run_b200(a):
     folded = load_weights()
     ev = BatchedPolicy(folded, dev, torch.float32)
     eng = MctsEngine(G, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=-1, device=dev, seed=a.seed,
-                     game_id_base=rank * G, game_id_stride=G * world, lanes=a.lanes, max_inline_sims=a.max_inline,
-                     out_pos_cap=G * 160, out_game_cap=2 * G + 64, node_cap=a.node_cap or None)
+                     game_id_base=rank * G, game_id_stride=G * world, lanes=a.lanes or None, max_inline_sims=a.max_inline,
+                     out_pos_cap=G * 160, out_game_cap=2 * G + 64, node_cap=a.node_cap or None,
+                     move_launch=None if a.move_launch < 0 else a.move_launch)
+    a.lanes = int(eng.cfg.lanes)
     run = SelfPlayRunner(eng, ev, use_graph=not a.no_graph)
     run.warm_start()
 
@@ -354,12 +350,12 @@ def run_b200(a):
         print(f"rank {rank} e2e stages (ms):", [(b[0], round((b[1] - a[1]) * 1e3, 1)) for a, b in zip(trace, trace[1:])], file=sys.stderr)
 
     # ---- roofline of the MCTS kernels: the library records CUDA events around the step kernel and around the
-    # move kernel of every launch (oth_mcts_profile_begin/_end), same pipeline, no graph
+    # move kernel of every launch (oth_mcts_profile_create / _read, othello_b200_experimental.h), same pipeline, no graph
     import ctypes as C
     torch.cuda.synchronize(dev)
     c0 = eng.counters()
     gap_cycles = int(float(os.environ.get("OTH_BENCH_GAP_US", "0")) * 1400)
-    _lib.check(_lib.lib().oth_mcts_profile_begin(iters))
+    eng.profile_begin(iters)
     for i in range(iters):
         if run.fused:  # same launch as in the timed region: softmax / tanh fused into the step kernel
             lg, vp = ev.raw(eng.nn_input)
@@ -369,13 +365,11 @@ def run_b200(a):
         else:
             ev(eng.nn_input, eng.priors, eng.values)
             eng.step()
-    step_ms, move_ms, n_rec = (C.c_float * iters)(), (C.c_float * iters)(), C.c_int32(0)
-    _lib.check(_lib.lib().oth_mcts_profile_end(step_ms, move_ms, C.byref(n_rec)))
+    kms_seq, mms_seq = eng.profile_end()
     torch.cuda.synchronize(dev)
-    assert n_rec.value == iters
+    assert len(kms_seq) == iters
     c1 = eng.counters()
     dk = {k: c1[k] - c0[k] for k in c1}
-    kms_seq, mms_seq = list(step_ms), list(move_ms)
     if os.environ.get("OTH_BENCH_DUMP_LAUNCHES"):
         json.dump({"step_ms": kms_seq, "move_ms": mms_seq}, open(os.environ["OTH_BENCH_DUMP_LAUNCHES"], "w"))
     kms = sorted(kms_seq)
@@ -414,7 +408,7 @@ def run_b200(a):
                        "network_twin": {"residual_conv": "one cuDNN graph relu(bias(conv+residual)) per block" if fused_plans
                                         else "cuDNN conv + k_bias_add_relu_bf16", "cudnn_plans": fused_plans},
                        "roofline_timing": "CUDA events recorded by the library on the launching stream around k_mcts_step and around "
-                                          "k_mcts_move of every launch (oth_mcts_profile_begin/_end) in an un-graphed pass of "
+                                          "k_mcts_move of every launch (oth_mcts_profile_create / _read, othello_b200_experimental.h) in an un-graphed pass of "
                                           "iters_per_step iterations of the same pipeline right after the timed region "
                                           "(events cannot be recorded inside the replayed graph)"},
             "positions_per_s": moves_total / (ms * 1e-3),
@@ -652,7 +646,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--games", type=int, default=0, help="override concurrent games per GPU")
     ap.add_argument("--iters-per-step", type=int, default=0)
-    ap.add_argument("--lanes", type=int, default=8)
+    ap.add_argument("--lanes", type=int, default=0, help="threads per game slot: 8 / 16 / 32 (0 = engine default for the slot count)")
+    ap.add_argument("--move-launch", type=int, default=-1, help="move kernel: 0 host-launched flag scan, 1 device tail launch (-1 = engine default)")
     ap.add_argument("--max-inline", type=int, default=8)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--node-cap", type=int, default=0, help="experiment: arena size per slot (default 48*sims+1024)")

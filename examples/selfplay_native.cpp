@@ -45,6 +45,8 @@ int main(int argc, char** argv)
     cfg.self_play = 1;
     cfg.max_inline_sims = 16;
     cfg.lanes = 8;
+    cfg.split_stub = 1;   // the production kernel pair (hot step kernel + move kernel) with the stub in the network's place
+    cfg.move_launch = 1;  // the step kernel launches the move kernel from the device when a move is due
     cfg.out_game_cap = (int64_t)cfg.n_slots * cfg.games_per_slot + 16;
     cfg.out_pos_cap = cfg.out_game_cap * 72;
     cfg.c_puct = 2.0;
@@ -60,6 +62,7 @@ int main(int argc, char** argv)
     int64_t bytes[OTH_BUF_COUNT];
     CHECK(oth_mcts_buffer_bytes(&cfg, bytes));
     oth_mcts_buffers bufs;
+    memset(&bufs, 0, sizeof(bufs));  // .profile = NULL: no launch timing
     size_t total = 0;
     for (int i = 0; i < OTH_BUF_COUNT; i++) {
         const size_t nb = bytes[i] > 0 ? (size_t)bytes[i] : 256;

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OTH_ABI_VERSION 1
+#define OTH_ABI_VERSION 2
 #define OTH_NUM_ACTIONS 65 /* envs/othello.py:325 action_size: 64 squares + pass */
 #define OTH_PASS 64
 #define OTH_MAX_PLIES 128 /* trace / trajectory rows per game */
@@ -54,8 +54,6 @@ int oth_abi_version(void);
 const char* oth_error_string(int code);
 const char* oth_last_cuda_error(void);
 int oth_device_count(void);
-/* cudaLimitMaxL2FetchGranularity for the current device: 32, 64 or 128 bytes (a hint). */
-int oth_set_l2_fetch_granularity(int32_t bytes);
 
 /* ------------------------------------------------------------------ env -- */
 
@@ -142,6 +140,9 @@ int oth_host_random_read_probe(int64_t buffer_bytes, int32_t chunk_bytes, double
 #define OTH_ERR_OUT_OVERFLOW 4
 #define OTH_ERR_PLY_OVERFLOW 8
 #define OTH_ERR_BAD_ACTION 16 /* MCTS.make_move KeyError, MCTS_model.py:214 */
+#define OTH_ERR_NONFINITE 32  /* the evaluator handed a NaN / infinite prior or value to this slot: the slot stops
+                                 (nothing non-finite ever enters a tree; the reference would carry on with NaN scores) */
+#define OTH_ERR_DEBUG 64      /* an index / ownership assertion of the -DOTH_DEBUG build failed */
 
 typedef struct oth_mcts_config {
     int32_t n_slots;          /* concurrent games on this GPU */
@@ -156,8 +157,17 @@ typedef struct oth_mcts_config {
     int32_t max_inline_sims;  /* simulations a slot may finish inside one launch without an
                                  external evaluation (terminal hits; all of them with a stub) */
     int32_t inject_random;    /* 1: read noise / u_move / u_tie from the buffers instead of Philox */
-    int32_t fused_softmax;    /* 1: `priors` holds logits; softmax is applied in-kernel */
     int32_t lanes;            /* threads cooperating on one slot: 8, 16 or 32 */
+    int32_t hot_path;         /* path entries carried in the 256-byte hot record (1..52, 0 = 52); deeper entries
+                                 live in OTH_BUF_PATH.  A tuning / test knob: small values force the HBM path tail */
+    int32_t split_stub;       /* device evaluators (OTH_EVAL_STUB_*) only.  0: one monolithic kernel runs whole
+                                 simulations back to back; 1: the production kernel pair -- the 64-register step
+                                 kernel expands with the stub's output, descends and parks the next leaf (one
+                                 evaluation per slot per launch), the move kernel plays the moves */
+    int32_t move_launch;      /* 0: the host launches the move kernel after every step kernel (it scans the move
+                                 flags); 1: the step kernel's last block launches it from the device
+                                 (cudaStreamTailLaunch) only when a move is due, one warp per due slot */
+    int32_t reserved0;
     int64_t out_pos_cap;      /* replay tuples the output ring can hold */
     int64_t out_game_cap;     /* finished-game descriptors it can hold */
     double c_puct;            /* args["c_puct"], MCTS_model.py:131,136 */
@@ -212,6 +222,8 @@ enum {
     OTH_BUF_SLOT_COUNTERS, /* uint32 [slot][16] cumulative per-slot event counters */
     OTH_BUF_HOT,         /* 256 B [slot]: pending leaf (board, legal set, meta), root header mirror, path[0..52) */
     OTH_BUF_MOVE_FLAGS,  /* uint8 [slot rounded up to 64]: slots whose move is due (step kernel -> move kernel) */
+    OTH_BUF_MOVE_LIST,   /* int32 [4 + n_slots]: [0] slots due, [1] step-kernel block tickets, [4..] the due slots
+                            (move_launch = 1: step kernel -> device-launched move kernel) */
     OTH_BUF_COUNT
 };
 
@@ -236,6 +248,7 @@ enum {
 
 typedef struct oth_mcts_buffers {
     void* buf[OTH_BUF_COUNT];
+    void* profile; /* NULL, or an oth_mcts_profile handle (othello_b200_experimental.h): per-engine launch timing */
 } oth_mcts_buffers;
 
 /* Sizes (bytes) of the OTH_BUF_* buffers for a configuration.  The caller allocates them in device
@@ -284,21 +297,17 @@ int oth_mcts_step_fused(const oth_mcts_config* cfg, const oth_mcts_buffers* b, c
                         const void* value_preact, int64_t value_stride, int32_t is_bf16, float* priors_out, float* values_out,
                         float* nn_input, void* stream);
 
-/* Per-launch kernel timing for benches (not thread-safe, one profile at a time): between _begin and _end every
- * oth_mcts_step / oth_mcts_step_fused call records CUDA events on its stream before the step kernel, after it and
- * after the move kernel (up to max_launches calls; do not use while the stream is being captured into a graph).
- * _end waits for the recorded launches and writes their durations in milliseconds: step_ms[i] = the step kernel,
- * move_ms[i] = the move kernel of call i (either may be NULL); *n_launches = calls recorded. */
-int oth_mcts_profile_begin(int32_t max_launches);
-int oth_mcts_profile_end(float* step_ms, float* move_ms, int32_t* n_launches);
-
 /* Refresh OTH_BUF_COUNTERS: sums the per-slot event counters and derives the gauges (WAITING /
  * ACTIVE / ERRORS / MAX_TOP) from the control blocks.  Kept out of the hot kernel; hosts call
  * it when they want totals or need to know whether to stop. */
 int oth_mcts_poll(const oth_mcts_config* cfg, const oth_mcts_buffers* b, void* stream);
 
 /* Manual mode: MCTS.make_move (MCTS_model.py:200-215) on every slot;
- * actions[slot] < 0 leaves that slot alone. */
+ * actions[slot] < 0 leaves that slot alone.  Root noise: the reference draws a fresh
+ * np.random.dirichlet whenever a search starts on an unexpanded root (MCTS_model.py:234-235, 339-343).
+ * When the new root is such a leaf and dirichlet_epsilon > 0, this call therefore replaces the slot's
+ * OTH_BUF_NOISE row with a fresh Philox draw keyed (seed; game id, ply) -- unless inject_random is set,
+ * in which case the HOST must write the row before the next oth_mcts_begin_search (the MCTS class does). */
 int oth_mcts_advance(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const int32_t* actions, void* stream);
 
 /* mcts.root.* as the reference exposes it: child visit counts / values /
@@ -333,13 +342,6 @@ int oth_nn_bias_add_relu_bf16(void* x, const void* res, const void* bias, int64_
  * (Models.py:105-107 / :179): float32 [n,64] -> bf16 [n,64,16] (9 taps + 7 zero columns), so the
  * stem runs as one GEMM with a fused bias+ReLU epilogue and writes channels-last output. */
 int oth_nn_stem_im2col_bf16(const float* planes, void* cols, int64_t n, void* stream);
-
-/* Network boundary helper: tells L2 that [ptr, ptr+bytes) is dead (an activation buffer whose last
- * consumer has run, e.g. the trunk output once the head GEMM has read it -- Models.py:213-219): its
- * cached lines are dropped without write-back (PTX discard.global.L2, whole 128-byte lines inside the
- * range only).  The contents of the range are undefined afterwards.  Must follow the last reader and
- * precede the next writer in stream order. */
-int oth_nn_l2_discard(void* ptr, int64_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

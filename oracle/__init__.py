@@ -76,6 +76,11 @@ def lib():
         L.orc_table_free.argtypes = [vp]
         L.orc_table_put.argtypes = [vp, C.c_uint64, C.c_uint64, vp, C.c_float]
         L.orc_table_put.restype = i32
+        L.orc_table_put_planes.argtypes = [vp, vp, vp, vp, vp, C.c_long, vp]
+        L.orc_table_put_planes.restype = i32
+        L.orc_mcts_set_picks.argtypes = [vp, vp, C.c_long]
+        L.orc_mcts_picks_used.argtypes = [vp]
+        L.orc_mcts_picks_used.restype = C.c_long
         L.orc_table_misses.argtypes = [vp]
         L.orc_table_misses.restype = C.c_long
         L.orc_table_hits.argtypes = [vp]
@@ -188,10 +193,22 @@ class EvalTable:
 
     def __init__(self, cap_pow2=1 << 20):
         self.handle = lib().orc_table_new(cap_pow2)
+        self.stats = np.zeros(3, np.int64)  # put_planes: inserted / identical repeats / conflicts
 
     def put(self, own, opp, priors, value):
         priors = np.ascontiguousarray(priors, dtype=np.float32)
         return lib().orc_table_put(self.handle, int(own), int(opp), _p(priors), float(value))
+
+    def put_planes(self, planes, mask, priors, values):
+        """One leaf batch: planes f32[n,64] canonical, mask uint8/bool[n] (rows to record), priors f32[n,65],
+        values f32[n].  Accumulates self.stats = [inserted, repeated identically, CONFLICTING]."""
+        planes = np.ascontiguousarray(planes, dtype=np.float32).reshape(-1, 64)
+        n = len(planes)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        priors = np.ascontiguousarray(priors, dtype=np.float32).reshape(n, 65)
+        values = np.ascontiguousarray(values, dtype=np.float32).reshape(n)
+        if lib().orc_table_put_planes(self.handle, _p(planes), _p(mask), _p(priors), _p(values), n, _p(self.stats)) != 0:
+            raise RuntimeError("EvalTable full")
 
     @property
     def misses(self):
@@ -213,12 +230,16 @@ class OracleMCTS:
     """MCTS surface (MCTS_model.py:172-274), num_threads=1 semantics, with
     the reference's np.random draws replaced by injected values."""
 
-    def __init__(self, c_puct, num_simulations, evaluator, dirichlet_epsilon=0.0, rollout_seed=0, game_id=0):
-        """evaluator=None selects the reference's policy=None mode (uniform priors + random playout)."""
+    def __init__(self, c_puct, num_simulations, evaluator, dirichlet_epsilon=0.0, rollout_seed=0, game_id=0, picks=None):
+        """evaluator=None selects the reference's policy=None mode (uniform priors + random playout); ``picks`` =
+        the indices np.random.choice returned in a reference run (else playouts draw from Philox)."""
         self.ev = evaluator
         if evaluator is None:
             self.h = lib().orc_mcts_new(float(c_puct), int(num_simulations), float(dirichlet_epsilon), None, None)
             lib().orc_mcts_set_rollout(self.h, int(rollout_seed), int(game_id))
+            if picks is not None:
+                self._picks = np.ascontiguousarray(picks, dtype=np.int32)
+                lib().orc_mcts_set_picks(self.h, _p(self._picks), len(self._picks))
         else:
             self.h = lib().orc_mcts_new(float(c_puct), int(num_simulations), float(dirichlet_epsilon),
                                         evaluator.fn_ptr, evaluator.ctx)
@@ -251,6 +272,10 @@ class OracleMCTS:
         if lib().orc_mcts_make_move(self.h, int(action)) != 0:
             raise KeyError(int(action))
         self.ply += 1
+
+    @property
+    def picks_used(self):
+        return lib().orc_mcts_picks_used(self.h)
 
     def root_stats(self):
         counts = np.zeros(65, np.int32)

@@ -12,15 +12,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _header_functions():
-    src = open(os.path.join(ROOT, "include", "othello_b200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(oth_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for h in ("othello_b200.h", "othello_b200_experimental.h"):  # the boundary + the measurement hooks
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(oth_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_library_builds_and_loads():
     path = build.build()
     assert os.path.exists(path)
-    assert _lib.lib().oth_abi_version() == 1
+    assert _lib.lib().oth_abi_version() == _lib.ABI_VERSION == 2
+    hdr = open(os.path.join(ROOT, "include", "othello_b200.h")).read()
+    assert re.search(r"#define OTH_ABI_VERSION 2\b", hdr)
 
 
 def test_every_header_symbol_is_exported_and_bound():
@@ -34,8 +39,15 @@ def test_every_header_symbol_is_exported_and_bound():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.MctsCtl) == 64
-    assert ctypes.sizeof(_lib.MctsConfig) == 12 * 4 + 2 * 8 + 5 * 8 + 4 * 8
-    assert ctypes.sizeof(_lib.MctsBuffers) == 8 * _lib.BUF_COUNT
+    assert ctypes.sizeof(_lib.MctsConfig) == 16 * 4 + 2 * 8 + 5 * 8 + 4 * 8
+    assert ctypes.sizeof(_lib.MctsBuffers) == 8 * (_lib.BUF_COUNT + 1)
+    # field order of the header's struct == the ctypes mirror
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "othello_b200.h")).read(), flags=re.S)
+    body = re.search(r"typedef struct oth_mcts_config \{(.*?)\} oth_mcts_config;", hdr, re.S).group(1)
+    fields = re.findall(r"\b(?:u?int(?:32|64)_t|double)\s+(\w+);", body)
+    assert fields == [f[0].rstrip("_") for f in _lib.MctsConfig._fields_]
+    buf_enum = re.search(r"enum \{\s*OTH_BUF_NODES = 0,(.*?)OTH_BUF_COUNT\b", hdr, re.S).group(1)
+    assert len(re.findall(r"OTH_BUF_\w+", buf_enum)) + 1 == _lib.BUF_COUNT
 
 
 def test_argument_validation_without_device():
@@ -50,6 +62,16 @@ def test_argument_validation_without_device():
     assert L.oth_mcts_buffer_bytes(ctypes.byref(cfg), sizes) == 0
     assert sizes[_lib.BUF_NODES] == 4 * 2 * 256 * 32 and sizes[_lib.BUF_BOARDS] == 4 * 2 * 256 * 16
     assert L.oth_error_string(_lib.OTH_E_ILLEGAL).decode() == "Illegal move"
+    cfg.hot_path = 53
+    assert L.oth_mcts_buffer_bytes(ctypes.byref(cfg), sizes) == _lib.OTH_E_ARG   # at most 52 entries fit the hot record
+    cfg.hot_path, cfg.split_stub = 4, 1
+    assert L.oth_mcts_buffer_bytes(ctypes.byref(cfg), sizes) == _lib.OTH_E_ARG   # split_stub needs a device stub evaluator
+    cfg.eval_kind = _lib.EVAL_STUB_H
+    assert L.oth_mcts_buffer_bytes(ctypes.byref(cfg), sizes) == 0
+    assert sizes[_lib.BUF_MOVE_LIST] == (4 + 4) * 4
+    h = ctypes.c_void_p()
+    assert L.oth_mcts_profile_create(0, ctypes.byref(h)) == _lib.OTH_E_ARG
+    assert L.oth_mcts_profile_read(None, None, None, None) == _lib.OTH_E_ARG
 
 
 def test_product_fails_loudly_without_gpu():

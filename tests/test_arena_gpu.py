@@ -83,3 +83,32 @@ def test_evaluate_models_parallel_signature():
                                       (FastOthelloNet, a.get_config(), a.state_dict()),
                                       (FastOthelloNet, b.get_config(), b.state_dict()), n_matches=8)
     assert 0.0 <= wa <= 1.0 and 0.0 <= wb <= 1.0 and wa + wb <= 1.0
+
+
+def test_batched_arena_reproduces_reference_matches(golden_r2):
+    """The match loop pinned to the reference itself: 11 matches that eval._run_one_match (eval.py:86-131, 134-178)
+    played on hash-stub policies -- even and odd match indices, wins for both sides, one drawn game -- with the tie
+    picks its np.random.choice(best_actions) calls made.  The batched arena, given the same device stubs and tie picks,
+    must return the same action at every ply and the same result string.  (Each reference match used its own pair of
+    stub salts; an engine has one salt, so match j is replayed as row j of a batch of j+1 concurrent matches.)"""
+    from alphazero_othello_b200.eval import DeviceStubPolicy, play_matches_batched
+    g = golden_r2
+    args = {"c_puct": float(g["ar_cfg"][1]), "num_simulations": int(g["ar_cfg"][0])}
+    seen = set()
+    for j, (idx, sa, sb, _seed, plies) in enumerate(g["ar_meta"]):
+        n = j + 1
+        u = np.zeros((n, 128))
+        u[j] = g["ar_u_tie"][j]
+        results, log = play_matches_batched(DeviceStubPolicy("H", sa), DeviceStubPolicy("H", sb), args, n, u_tie=u,
+                                            lanes=[8, 16, 32][j % 3])
+        assert log["plies"][j] == plies and list(log["actions"][j, :plies]) == list(g["ar_actions"][j, :plies]), j
+        assert results[j] == str(g["ar_results"][j]), j
+        seen.add(results[j])
+    assert seen == {"A", "B", "Draw"}
+    # play_match alone (first tree = +1): match 0 of a one-match batch
+    sa, sb = g["ar_direct_salts"]
+    u = g["ar_direct_u_tie"][None, :]
+    u = np.concatenate([u, np.zeros((1, 128 - u.shape[1]))], 1)
+    results, log = play_matches_batched(DeviceStubPolicy("H", sa), DeviceStubPolicy("H", sb), args, 1, u_tie=u)
+    k = len(g["ar_direct_actions"])
+    assert list(log["actions"][0, :k]) == list(g["ar_direct_actions"]) and results[0] == str(g["ar_direct_result"][0])

@@ -457,7 +457,11 @@ def test_randomised_hyper_parameters_vs_oracle(seed):
     lanes = int(rs.choice(LANES))
     salt = int(rs.randint(1, 1 << 30))
     n = 24
-    e = _selfplay_engine(args, lanes, n, False, salt, seed=int(rs.randint(1 << 30)), max_inline_sims=int(rs.choice([1, 4, 16, 1000])))
+    # kernel variant: monolithic device-evaluator kernel, or the production pair (step + move kernel) with the stub in the
+    # network's place, move kernel launched by the host or from the device, path tail forced into HBM or not
+    variant = dict(split_stub=bool(rs.randint(2)), move_launch=int(rs.randint(2)), hot_path=int(rs.choice([0, 0, 3, 9])))
+    e = _selfplay_engine(args, lanes, n, False, salt, seed=int(rs.randint(1 << 30)), max_inline_sims=int(rs.choice([1, 4, 16, 1000])),
+                         **variant)
     _run_to_done(e, max_launches=60000)
     noise = e.noise.cpu().numpy(); um = e.u_move.cpu().numpy(); ut = e.u_tie.cpu().numpy()
     out = e.drain()
@@ -479,27 +483,3 @@ def test_randomised_hyper_parameters_vs_oracle(seed):
         assert np.array_equal(np.array([t[2] for t in traj]), ref["values"]), (args, g)
         tot_sims += ref["counters"]["sims"]
     assert c["sims"] == tot_sims
-
-
-def test_launch_profile_records_step_and_move_kernels():
-    """oth_mcts_profile_begin/_end: one (step, move) duration pair per oth_mcts_step call, recording stops at the cap."""
-    import ctypes as C
-    from alphazero_othello_b200 import _lib
-    args = {"c_puct": 2.0, "num_simulations": 8, "dirichlet_alpha": 1.0, "dirichlet_epsilon": 0.3,
-            "mcts_temperature": 1.0, "num_exploratory_moves": 10, "lambda": 0.98}
-    from alphazero_othello_b200.engine import MctsEngine
-    e = MctsEngine(64, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=1)
-    e.priors.fill_(1.0 / 65)
-    e.reset()
-    L = _lib.lib()
-    assert L.oth_mcts_profile_begin(0) == _lib.lib().oth_mcts_profile_begin(-3) != 0  # argument check
-    _lib.check(L.oth_mcts_profile_begin(5))
-    for _ in range(7):
-        e.step()
-    step_ms, move_ms, n = (C.c_float * 5)(), (C.c_float * 5)(), C.c_int32(-1)
-    _lib.check(L.oth_mcts_profile_end(step_ms, move_ms, C.byref(n)))
-    assert n.value == 5
-    assert all(0.0 < t < 50.0 for t in step_ms) and all(0.0 < t < 50.0 for t in move_ms)
-    assert L.oth_mcts_profile_end(step_ms, move_ms, C.byref(n)) != 0  # nothing to end
-    e.step()  # launches keep working with profiling off
-    e.raise_on_error()

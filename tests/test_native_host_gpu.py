@@ -17,7 +17,8 @@ def test_native_cpp_host_plays_complete_games():
     exe = os.path.join(ROOT, "examples", "selfplay_native")
     src = exe + ".cpp"
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+    hdr = os.path.join(ROOT, "include", "othello_b200.h")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call([nvcc, "-O2", "-o", exe, src, "-L" + os.path.join(ROOT, "alphazero_othello_b200"), "-lothello_b200",
                                "-Xlinker", "-rpath", "-Xlinker", os.path.join(ROOT, "alphazero_othello_b200")])
     out = subprocess.run([exe, "512", "32", "2"], capture_output=True, text=True, timeout=300)

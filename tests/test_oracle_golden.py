@@ -145,3 +145,80 @@ def test_philox_known_answer():
     # all-ones counter and key (Random123 kat_vectors)
     full = (1 << 64) - 1
     assert [hex(int(x)) for x in O.philox(full, full, 0xffffffff, 0xffffffff)] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+
+
+# ------------------------------------------------------------ round 2: M13 rollouts and the arena, pinned to the reference
+@pytest.mark.parametrize("case", ["ro0", "ro1", "ro2"])
+def test_rollout_mode_matches_reference_on_its_own_picks(golden_r2, case):
+    """policy=None (MCTS_model.py:276-303, 332-335): uniform priors, value = outcome of a random playout seen from the
+    leaf's side to move.  The oracle consumes the indices the reference's np.random.choice calls returned (forced
+    passes draw nothing) and must reproduce every visit count, child value and root value of the reference run."""
+    g = golden_r2
+    sims, c = g[case + "_cfg"]
+    m = O.OracleMCTS(float(c), int(sims), None, picks=g[case + "_picks"])
+    for t in range(len(g[case + "_action"])):
+        m.search(g[case + "_state"][t], int(g[case + "_player"][t]))
+        r = m.root_stats()
+        assert np.array_equal(r["counts"], g[case + "_counts"][t]), (case, t)
+        assert np.array_equal(r["child_value"], g[case + "_cval"][t]), (case, t)
+        assert r["root_value"] == g[case + "_root_value"][t] and r["root_n"] == g[case + "_root_n"][t]
+        assert m.picks_used == g[case + "_picks_after"][t]  # the same number of draws, search by search
+        m.make_move(int(g[case + "_action"][t]))
+    assert m.picks_used == len(g[case + "_picks"])
+
+
+def oracle_play_match(first, second, u_tie, max_plies=128):
+    """eval.play_match (eval.py:134-178) on two OracleMCTS trees with the reference's tie picks injected: the mover's
+    tree searches with temp=0, arg-max move, BOTH trees follow it.  Returns (result, actions) -- the golden test
+    below checks this loop against what the reference's own play_match / _run_one_match returned."""
+    game = O.OracleGame(8)
+    state, player = game.get_initial_state(), 1
+    actions = []
+    searched = {id(first): False, id(second): False}
+    for ply in range(max_plies):
+        if game.get_valid_moves(state, player).sum() == 0:
+            return "Draw", actions
+        tree = first if player == 1 else second
+        probs = tree.policy_improve_step(state, player, temp=0.0, u_tie=float(u_tie[ply]))
+        searched[id(tree)] = True
+        action = int(np.argmax(probs))
+        actions.append(action)
+        state = game.get_next_state(state, action, player)
+        reward, done = game.get_value_and_terminated(state, action, player)
+        if done:
+            if reward == 1:
+                return ("A" if player == 1 else "B"), actions
+            if reward == -1:
+                return ("B" if player == 1 else "A"), actions
+            return "Draw", actions
+        for t in (first, second):
+            if searched[id(t)]:  # make_move before the first own search is a no-op (MCTS_model.py:209-211)
+                t.make_move(action)
+        player = -player
+    raise AssertionError("match did not end")
+
+
+def _arena_trees(cfg, salt_first, salt_second):
+    sims, c = int(cfg[0]), float(cfg[1])
+    return (O.OracleMCTS(c, sims, O.Evaluator(stub=O.STUB_H, salt=int(salt_first))),
+            O.OracleMCTS(c, sims, O.Evaluator(stub=O.STUB_H, salt=int(salt_second))))
+
+
+def test_arena_matches_reference_results_and_actions(golden_r2):
+    """eval._run_one_match (eval.py:86-131): even match index -> the candidate's tree plays +1, odd -> the incumbent's,
+    and the result is inverted back to the candidate's point of view.  Actions of every ply and the result string of
+    11 reference matches (even and odd indices, wins for both sides, one drawn game)."""
+    g = golden_r2
+    res = list(g["ar_results"])
+    assert "Draw" in res and "A" in res and "B" in res
+    for j, (idx, sa, sb, _seed, plies) in enumerate(g["ar_meta"]):
+        assert idx == j
+        first, second = _arena_trees(g["ar_cfg"], sa if idx % 2 == 0 else sb, sb if idx % 2 == 0 else sa)
+        r, acts = oracle_play_match(first, second, g["ar_u_tie"][j])
+        if idx % 2 == 1 and r != "Draw":
+            r = "B" if r == "A" else "A"
+        assert acts == list(g["ar_actions"][j, :plies]), j
+        assert r == res[j], j
+    first, second = _arena_trees(g["ar_cfg"], *g["ar_direct_salts"])  # play_match alone: A = the tree that plays +1
+    r, acts = oracle_play_match(first, second, g["ar_direct_u_tie"])
+    assert r == g["ar_direct_result"][0] and acts == list(g["ar_direct_actions"])

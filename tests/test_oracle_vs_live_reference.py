@@ -260,3 +260,49 @@ def test_replay_aggregation_side_by_side(ref, seed):
     assert np.array_equal(np.stack(states), np.stack(o_states))
     assert np.array_equal(np.stack(policies).astype(np.float32), np.stack(o_policies))
     assert np.array_equal(np.array(values, np.float32), np.array(o_values, np.float32))
+
+
+@pytest.mark.parametrize("seed,sims,c_puct,moves", [(21, 40, 1.4, 5), (22, 15, 3.0, 30), (23, 90, 1.0, 3)])
+def test_rollout_mode_side_by_side(ref, monkeypatch, seed, sims, c_puct, moves):
+    """policy=None (MCTS_model.py:276-303, 332-335) live: the reference's playouts draw np.random.choice(possible_actions);
+    the returned indices are tapped and handed to the oracle, which must then build the identical tree -- uniform
+    np.ones(65) priors masked and normalised, playout value seen from the leaf's side to move, forced passes drawing
+    nothing -- over several moves with tree re-use."""
+    import oracle as O
+    g = ref["Game"](8)
+    real_choice = np.random.choice
+    picks = []
+
+    def choice(a, *k, **kw):
+        r = real_choice(a, *k, **kw)
+        arr = [int(x) for x in np.asarray(a)]
+        if arr != [64]:
+            picks.append(arr.index(int(r)))
+        return r
+
+    monkeypatch.setattr(np.random, "choice", choice)
+    np.random.seed(seed)
+    m = ref["MCTS"](g, {"c_puct": c_puct, "num_simulations": sims, "num_threads": 1}, None)
+    s, player = g.get_initial_state(), 1
+    per_move = []
+    for mv in range(moves):
+        probs = m.policy_improve_step(s, player, temp=1.0)
+        counts = np.zeros(65, np.int32)
+        cval = np.zeros(65)
+        for a, ch in m.root.children.items():
+            counts[a], cval[a] = ch.visit_count, ch.value
+        a = int(np.argmax(probs))
+        per_move.append((s.copy(), player, counts, cval, m.root.value, m.root.visit_count, len(picks), a, probs.copy()))
+        m.make_move(a)
+        s = g.get_next_state(s, a, player)
+        if g.get_value_and_terminated(s, a, player)[1]:
+            break
+        player = -player
+    om = O.OracleMCTS(c_puct, sims, None, picks=np.array(picks, np.int32))
+    for s, player, counts, cval, rv, rn, used, a, probs in per_move:
+        assert np.array_equal(om.policy_improve_step(s, player, temp=1.0), probs)
+        r = om.root_stats()
+        assert np.array_equal(r["counts"], counts) and np.array_equal(r["child_value"], cval)
+        assert r["root_value"] == rv and r["root_n"] == rn and om.picks_used == used
+        om.make_move(a)
+    assert om.picks_used == len(picks)
