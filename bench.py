@@ -103,6 +103,108 @@ def cpu_env_rate(cores, seconds=2.0):
     return sum(r[0] for r in res) / max(r[2] for r in res), sum(r[1] for r in res)
 
 
+# ------------------------------------------------- the reference itself -----
+# baseline/_ref/ holds the reference's own, unmodified hot-path sources (tools/stage_reference.sh; git-ignored, ships
+# to the GPU box).  The arm below drives them exactly as Trainer.collect_self_play_games does (train.py:199-225): a
+# spawn Pool of one process per host core, initialised by the reference's eval._worker_init, each task one
+# one_self_play((board_size, args, (policy_class, policy_config, state_dict), cache)) with the default num_threads (4)
+# and OMP_NUM_THREADS=1 (MCTS_model.py:3).  A whole game at 400 simulations x ~60 plies takes minutes per core, so a
+# task is stopped after a fixed number of plies: two counting wrappers are put around MCTS._simulate (simulations
+# completed) and MCTS.policy_improve_step (plies searched; raises after the budget) -- the reference's code is not edited.
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+REF_PLIES_PER_STEP = {"c4": 2, "c3": 6, "c2": 12}
+
+
+def reference_available():
+    return os.path.exists(os.path.join(REF_DIR, "self_play_worker.py"))
+
+
+class _PlyBudget(Exception):
+    pass
+
+
+_REF = {}
+
+
+def _ref_worker_init(seed_base):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF_DIR)
+    import MCTS_model
+    import self_play_worker
+    import eval as ref_eval
+    ref_eval._worker_init(seed_base)  # the reference's own per-process seeding (eval.py:77-84)
+    st = {"sims": 0, "plies": 0, "budget": 1 << 30}
+    sim, pis = MCTS_model.MCTS._simulate, MCTS_model.MCTS.policy_improve_step
+
+    def counted_simulate(self, root):
+        r = sim(self, root)
+        st["sims"] += 1
+        return r
+
+    def budgeted_pis(self, init_state, init_player, temp=1):
+        if st["plies"] >= st["budget"]:
+            raise _PlyBudget()
+        st["plies"] += 1
+        return pis(self, init_state, init_player, temp=temp)
+
+    MCTS_model.MCTS._simulate, MCTS_model.MCTS.policy_improve_step = counted_simulate, budgeted_pis
+    _REF.update(st=st, one_self_play=self_play_worker.one_self_play)
+
+
+def _ref_task(job):
+    args_tuple, plies = job
+    st = _REF["st"]
+    st.update(sims=0, plies=0, budget=plies)
+    t0 = time.perf_counter()
+    try:
+        _REF["one_self_play"](args_tuple)  # returns only if the game ended inside the budget
+    except _PlyBudget:
+        pass
+    return st["sims"], st["plies"], time.perf_counter() - t0
+
+
+def reference_rate(workload, steps, warm, cores):
+    """The unmodified reference's one_self_play on all host cores.  Returns (sims/s, ms per step, description)."""
+    import multiprocessing as mp
+    desc, kind, G, sims = WORKLOADS[workload]
+    plies = REF_PLIES_PER_STEP[workload]
+    os.environ["OMP_NUM_THREADS"] = "1"
+    sys.path.insert(0, REF_DIR)
+    try:
+        import torch
+        import Models as RefModels  # baseline/_ref/Models.py
+        torch.manual_seed(0)
+        net = RefModels.AlphaZeroNet(8, 65, 5, 128) if kind == "big" else RefModels.FastOthelloNet(8, 65)
+        policy_state = (net.__class__, net.get_config(), net.state_dict())
+    finally:
+        sys.path.remove(REF_DIR)
+    args = dict(TRAIN_ARGS, num_simulations=sims)  # no "num_threads": the reference's default of 4 applies
+    job = ((8, args, policy_state, None), plies)
+    per_step = []
+    with mp.get_context("spawn").Pool(cores, initializer=_ref_worker_init, initargs=(12345,)) as pool:
+        for i in range(warm + steps):
+            t0 = time.perf_counter()
+            res = pool.map(_ref_task, [job] * cores, chunksize=1)
+            per_step.append((sum(r[0] for r in res), time.perf_counter() - t0))
+    timed = per_step[warm:]
+    total_sims, total_s = sum(s for s, _ in timed), sum(t for _, t in timed)
+    sample = (f"per step every one of {cores} spawn-Pool processes runs the unmodified reference one_self_play "
+              f"(baseline/_ref, default num_threads=4, OMP_NUM_THREADS=1, f32 torch CPU network at batch 1) for the first "
+              f"{plies} plies of a game ({sims} simulations each); step time = wall clock until the slowest process returns")
+    return total_sims / total_s, 1e3 * total_s / len(timed), sample
+
+
+def workload_config(workload, G, sims, iters):
+    """What is computed -- identical in the B200 arm and in the reference arm (the driver compares the two)."""
+    node_cap = max(2048, 48 * sims + 1024)
+    return {"workload": f"{workload}: {WORKLOADS[workload][0]}", "net": WORKLOADS[workload][1], "games_per_gpu": G,
+            "sims_per_move": sims, "iters_per_step": iters,
+            "l2": f"inputs larger than L2: tree arenas {G * 2 * node_cap * 48 >> 20} MiB per GPU vs 126 MB L2 (no flush needed)"
+                  if G * 2 * node_cap * 48 > (256 << 20) else
+                  "working set fits L2 by construction of this config; L2 is flushed by the network's activations between launches"}
+
+
 # ---------------------------------------------------------------- utilities --
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -401,9 +503,9 @@ def run_b200(a):
             "unit": "sims/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 search (u64 boards), bf16 network",
             "data": "synthetic: self-play from the initial position, random-init weights (torch.manual_seed(0))",
-            "config": {"workload": f"{a.workload}: {desc}", "net": kind, "games_per_gpu": G, "sims_per_move": sims,
-                       "iters_per_step": iters, "lanes": a.lanes, "cuda_graph": not a.no_graph,
-                       "l2": f"tree arenas {eng.buf_bytes[0] + eng.buf_bytes[1] >> 20} MiB per GPU >> 126 MB L2 (inputs larger than L2)",
+            "config": workload_config(a.workload, G, sims, iters),
+            "engine": {"lanes": a.lanes, "cuda_graph": not a.no_graph, "move_launch": int(eng.cfg.move_launch),
+                       "arena_mib": eng.buf_bytes[0] + eng.buf_bytes[1] >> 20,
                        "sharding": "games by id, no collective on the search path",
                        "network_twin": {"residual_conv": "one cuDNN graph relu(bias(conv+residual)) per block" if fused_plans
                                         else "cuDNN conv + k_bias_add_relu_bf16", "cudnn_plans": fused_plans},
@@ -418,6 +520,8 @@ def run_b200(a):
                                 "D2H of policy targets/root values and finished games' replay tuples (+gather to rank 0)"},
             # this repo's kernels per iteration: k_mcts_step, k_mcts_move, k_stem_im2col_bf16 and -- only when the
             # residual convolutions do not run as one cuDNN graph -- one k_bias_add_relu_bf16 per residual block
+            # (with move_launch = 1 the move kernel is launched from the device only in iterations where a move is due:
+            # counted as one per iteration all the same, an upper bound)
             "gpu_launches": a.steps * iters * (3 + (0 if fused_plans else (5 if kind == "big" else 1))),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": f"k_mcts_step{'_fused' if run.fused else ''}<{a.lanes}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -669,18 +773,25 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        import oracle
-        oracle.build()
-        rate, ms_step, wall = cpu_port_rate(kind, sims, a.steps, a.warmup, cores)
-        sample = f"per step every core runs one policy_improve_step of {sims} simulations from the initial position " \
-                 f"(batch-1 torch CPU forward per simulation), {cores} processes"
+        iters = a.iters_per_step or sims
+        G_ref = a.games or G
+        if reference_available() and not os.environ.get("OTH_BENCH_FORCE_PORT"):
+            rate, ms_step, sample = reference_rate(a.workload, a.steps, a.warmup, cores)
+            ref_kind = "reference"
+        else:  # no staged reference on this box: the oracle port (C tree/env + the same torch net at batch 1)
+            import oracle
+            oracle.build()
+            rate, ms_step, wall = cpu_port_rate(kind, sims, a.steps, a.warmup, cores)
+            sample = f"per step every core runs one policy_improve_step of {sims} simulations from the initial position " \
+                     f"(batch-1 torch CPU forward per simulation), {cores} processes"
+            ref_kind = "port"
         print(json.dumps({
             "impl": "reference", "metric": "MCTS simulations/s (self-play, one network evaluation per simulation)",
             "value": rate, "unit": "sims/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 search, f32 network (CPU)",
             "data": "synthetic: random-init weights (torch.manual_seed(0))",
-            "config": {"workload": f"{a.workload}: {desc}", "net": kind, "sims_per_move": sims},
-            "cpu_baseline": {"value": rate, "unit": "sims/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(a.workload, G_ref, sims, iters),
+            "cpu_baseline": {"value": rate, "unit": "sims/s", "cores": cores, "kind": ref_kind, "sample": sample},
             "e2e": {"value": rate, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}), file=result_out, flush=True)
         return
@@ -703,9 +814,15 @@ def main():
             import oracle
             oracle.build()
             rate, ms_step, wall = cpu_port_rate(kind, sims, 2, 1, cores)
-            out["cpu_baseline"] = {"value": rate, "unit": "sims/s", "cores": cores, "kind": "port",
-                                   "sample": f"{cores} processes x 2 searches of {sims} simulations from the initial position "
-                                             f"(oracle C tree/env + batch-1 torch CPU forward of the {kind} net), {wall:.1f} s wall"}
+            port = {"value": rate, "unit": "sims/s", "cores": cores, "kind": "port",
+                    "sample": f"{cores} processes x 2 searches of {sims} simulations from the initial position "
+                              f"(oracle C tree/env + batch-1 torch CPU forward of the {kind} net), {wall:.1f} s wall"}
+            if reference_available():
+                rate, ms_step, sample = reference_rate(a.workload, 2, 1, cores)
+                out["cpu_baseline"] = {"value": rate, "unit": "sims/s", "cores": cores, "kind": "reference", "sample": sample,
+                                       "port": port}
+            else:
+                out["cpu_baseline"] = port
         else:
             out["cpu_baseline"] = None
         print(json.dumps(out), file=result_out, flush=True)
