@@ -20,11 +20,10 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "--fmad=false",            # numpy rounds every float op: no FMA contraction anywhere
-    "-rdc=true",               # the step kernel tail-launches the move kernel from the device (CUDA dynamic parallelism)
     "-Xcompiler", "-fPIC", "-shared",
     "-Xptxas", "-v",
 ]
-LINK_FLAGS = ["-lcudadevrt", "-ldl"]
+LINK_FLAGS = ["-ldl"]
 
 
 def _nvcc():

@@ -36,7 +36,7 @@ namespace {
 
 constexpr int kBlock = 128;
 #ifndef OTH_STEP_BLOCKS_PER_SM
-#define OTH_STEP_BLOCKS_PER_SM 7
+#define OTH_STEP_BLOCKS_PER_SM 8
 #endif
 constexpr int kStepBlocksPerSM = OTH_STEP_BLOCKS_PER_SM;  // resident step-kernel blocks per SM the register budget is sized for
 constexpr int kMoveSet = 8;  // slots per warp in k_mcts_move
@@ -1160,7 +1160,9 @@ struct Ctx {
                     c.phase = OTH_PH_MOVE;  // the move kernel of this same step takes over
                     if (lane == 0) {
                         P.move_flags[slot] = 1;
-                        if (P.cfg.move_launch) P.move_list[4 + atomicAdd(P.move_list, 1)] = slot;
+                        if (P.cfg.move_launch) {
+                            P.move_list[4 + atomicAdd(P.move_list, 1)] = slot;
+                        }
                     }
                     break;
                 }
@@ -1233,36 +1235,6 @@ struct Ctx {
     }
 };
 
-__global__ void k_mcts_move_list(const Params P, const int n_due);
-
-// cfg.move_launch = 1: the last block of a step kernel to finish launches the move kernel from the device, after
-// the step grid (cudaStreamTailLaunch), and only if some slot's move is due -- one warp per due slot, no flag scan,
-// nothing at all in the common launch where no slot moves.  Stream order is kept: the step grid is not complete
-// for the next kernel in the stream until its tail launch has completed.
-__device__ __noinline__ void launch_move_from_device(const Params& P, int n)
-{
-    const int blocks = (n + kBlock / 32 - 1) / (kBlock / 32);
-    k_mcts_move_list<<<blocks, kBlock, 0, cudaStreamTailLaunch>>>(P, n);
-}
-
-__device__ __forceinline__ void step_tail(const Params& P)
-{
-#ifndef OTH_NO_TAIL
-    if (!P.cfg.move_launch) return;
-    __syncthreads();  // every group of this block has appended its due slot
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const int t = atomicAdd(P.move_list + 1, 1);
-        if (t == (int)gridDim.x - 1) {
-            __threadfence();
-            const int n = atomicExch(P.move_list, 0);
-            P.move_list[1] = 0;
-            if (n > 0) launch_move_from_device(P, n);
-        }
-    }
-#endif
-}
-
 // The hot kernel (external network): expansion, backup, descent.  Moves are only flagged.
 template <int LANES>
 __global__ void __launch_bounds__(kBlock, kStepBlocksPerSM) k_mcts_step(const Params P)
@@ -1275,7 +1247,6 @@ __global__ void __launch_bounds__(kBlock, kStepBlocksPerSM) k_mcts_step(const Pa
         ctx.slot = s;
         ctx.template run_slot<false, false>();
     }
-    step_tail(P);
 }
 
 // The hot kernel with a device stub in the network's place (cfg.split_stub): search-only runs and parity tests of
@@ -1291,7 +1262,6 @@ __global__ void __launch_bounds__(kBlock, kStepBlocksPerSM) k_mcts_step_devstub(
         ctx.slot = s;
         ctx.template run_slot<false, false, false, true>();
     }
-    step_tail(P);
 }
 
 // The hot kernel with the network's softmax / tanh fused in (oth_mcts_step_fused).
@@ -1306,7 +1276,6 @@ __global__ void __launch_bounds__(kBlock, kStepBlocksPerSM) k_mcts_step_fused(co
         ctx.slot = s;
         ctx.template run_slot<false, false, true>();
     }
-    step_tail(P);
 }
 
 // Device-evaluator build (stubs / rollouts): everything in one kernel, whole simulations per launch.
@@ -1350,11 +1319,20 @@ __global__ void __launch_bounds__(kBlock) k_mcts_move(const Params P)
     }
 }
 
-// The move kernel as launched from the device (step_tail): one warp per due slot, slots taken from the list
-// the step kernel wrote.
-__global__ void __launch_bounds__(kBlock) k_mcts_move_list(const Params P, const int n_due)
+// The move kernel, due-list form (cfg.move_launch = 1): the step kernel appended every slot whose move is due to
+// OTH_BUF_MOVE_LIST.  A block reads the count first and exits at once when it is zero -- the common launch, in which no
+// slot moves, costs one 4-byte load per block instead of a scan of the move flags -- otherwise one warp takes one due
+// slot (no scan, and the launch in which every slot moves is spread evenly).  The last block to finish resets the list.
+// (A device-side tail launch of this kernel from the step kernel was tried and removed: inside a captured CUDA graph the
+// child grid is not ordered before the next graph launch, so its control-block updates raced with the next step kernel.)
+__global__ void __launch_bounds__(kBlock) k_mcts_move_list(const Params P)
 {
     __shared__ Scratch scratch[kBlock / 32];
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = *reinterpret_cast<volatile int*>(P.move_list);
+    __syncthreads();
+    const int n_due = s_n;
+    if (n_due == 0) return;
     cg::thread_block_tile<32> tile = cg::tiled_partition<32>(cg::this_thread_block());
     Ctx<32> ctx(tile, P, scratch[threadIdx.x / 32]);
     const int warps = (gridDim.x * kBlock) / 32;
@@ -1363,6 +1341,14 @@ __global__ void __launch_bounds__(kBlock) k_mcts_move_list(const Params P, const
         ctx.template run_slot<true, false>();
         if ((threadIdx.x & 31) == 0) P.move_flags[ctx.slot] = 0;
         __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(P.move_list + 1, 1) == (int)gridDim.x - 1) {  // every block has read the count: reset for the next step kernel
+            P.move_list[0] = 0;
+            P.move_list[1] = 0;
+        }
     }
 }
 
@@ -1767,11 +1753,17 @@ extern "C" int oth_mcts_profile_destroy(void* handle)
     return OTH_OK;
 }
 
-// The move kernel after a step kernel: host-launched flag scan (move_launch = 0) or nothing here (the step
-// kernel's last block tail-launches k_mcts_move_list when a move is due).
+// The move kernel after a step kernel: flag scan (move_launch = 0) or due list (1).
 static inline void launch_move(const oth_mcts_config* cfg, const Params& p, void* stream)
 {
-    if (cfg->self_play && !cfg->move_launch) k_mcts_move<<<move_grid(cfg), kBlock, 0, (cudaStream_t)stream>>>(p);
+    if (!cfg->self_play) return;
+    if (cfg->move_launch) {
+        const int blocks = (cfg->n_slots + kBlock / 32 - 1) / (kBlock / 32);  // a warp per slot if every slot is due
+        const int cap = sm_count() * 4;
+        k_mcts_move_list<<<blocks < cap ? blocks : cap, kBlock, 0, (cudaStream_t)stream>>>(p);
+    } else {
+        k_mcts_move<<<move_grid(cfg), kBlock, 0, (cudaStream_t)stream>>>(p);
+    }
 }
 
 extern "C" int oth_mcts_step(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const float* priors, const float* values,

@@ -298,6 +298,10 @@ class SelfPlayRunner:
         ``engine.values`` (fused path: what the kernel's own softmax / tanh produced), so a checker can replay them."""
         self.e = engine
         self.record = record
+        # diagnostic hooks, called around every EXECUTED iteration (eager ones, the warm-up iterations of the graph
+        # capture, graph replays): a checker snapshots the leaf batch before and the consumed outputs after
+        self.before_iteration = None
+        self.after_iteration = None
         self.evaluator = evaluator
         self.external = engine.cfg.eval_kind == _lib.EVAL_EXTERNAL
         assert not self.external or evaluator is not None
@@ -328,12 +332,19 @@ class SelfPlayRunner:
         s.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(s):
             for _ in range(2):  # executed (they are real iterations), so lazy initialisation is done before capture
-                self._iteration()
+                self._hooked(self._iteration)
         torch.cuda.current_stream(dev).wait_stream(s)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._iteration()  # recorded, not executed
         self.graph = g
+
+    def _hooked(self, fn):
+        if self.before_iteration is not None:
+            self.before_iteration()
+        fn()
+        if self.after_iteration is not None:
+            self.after_iteration()
 
     def run_iterations(self, n):
         """n x (network forward over the leaf batch + one fused MCTS kernel launch), as CUDA-graph replays."""
@@ -342,10 +353,10 @@ class SelfPlayRunner:
         torch.cuda.nvtx.range_push(f"selfplay:{n} iterations (network + oth_mcts_step)")
         for _ in range(n):
             if self.graph is not None:
-                self.graph.replay()
+                self._hooked(self.graph.replay)
                 self.e.launches += 1
             else:
-                self._iteration()
+                self._hooked(self._iteration)
         torch.cuda.nvtx.range_pop()
 
     def play(self, check_every=64, max_iterations=None):

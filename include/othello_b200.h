@@ -164,9 +164,9 @@ typedef struct oth_mcts_config {
                                  simulations back to back; 1: the production kernel pair -- the 64-register step
                                  kernel expands with the stub's output, descends and parks the next leaf (one
                                  evaluation per slot per launch), the move kernel plays the moves */
-    int32_t move_launch;      /* 0: the host launches the move kernel after every step kernel (it scans the move
-                                 flags); 1: the step kernel's last block launches it from the device
-                                 (cudaStreamTailLaunch) only when a move is due, one warp per due slot */
+    int32_t move_launch;      /* form of the move kernel that follows every step kernel.  0: it scans the move flags;
+                                 1: the step kernel lists the due slots, the move kernel exits at once when the list
+                                 is empty and otherwise gives one warp to each listed slot */
     int32_t reserved0;
     int64_t out_pos_cap;      /* replay tuples the output ring can hold */
     int64_t out_game_cap;     /* finished-game descriptors it can hold */
@@ -222,8 +222,8 @@ enum {
     OTH_BUF_SLOT_COUNTERS, /* uint32 [slot][16] cumulative per-slot event counters */
     OTH_BUF_HOT,         /* 256 B [slot]: pending leaf (board, legal set, meta), root header mirror, path[0..52) */
     OTH_BUF_MOVE_FLAGS,  /* uint8 [slot rounded up to 64]: slots whose move is due (step kernel -> move kernel) */
-    OTH_BUF_MOVE_LIST,   /* int32 [4 + n_slots]: [0] slots due, [1] step-kernel block tickets, [4..] the due slots
-                            (move_launch = 1: step kernel -> device-launched move kernel) */
+    OTH_BUF_MOVE_LIST,   /* int32 [4 + n_slots]: [0] slots due, [1] move-kernel block tickets, [4..] the due slots
+                            (move_launch = 1: step kernel -> move kernel) */
     OTH_BUF_COUNT
 };
 

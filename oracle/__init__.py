@@ -22,7 +22,7 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 EVAL_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_int8), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double))
 
-STUB_A, STUB_B, STUB_H, STUB_TABLE = 0, 1, 2, 3
+STUB_A, STUB_B, STUB_H, STUB_TABLE, STUB_TAPE = 0, 1, 2, 3, 4
 
 
 def build(force=False):
@@ -81,6 +81,13 @@ def lib():
         L.orc_mcts_set_picks.argtypes = [vp, vp, C.c_long]
         L.orc_mcts_picks_used.argtypes = [vp]
         L.orc_mcts_picks_used.restype = C.c_long
+        L.orc_tape_new.argtypes = [C.c_long, C.c_long]
+        L.orc_tape_new.restype = vp
+        L.orc_tape_free.argtypes = [vp]
+        L.orc_tape_put_planes.argtypes = [vp, vp, vp, vp, vp, C.c_long]
+        L.orc_tape_put_planes.restype = i32
+        L.orc_tape_stat.argtypes = [vp, C.c_long, i32]
+        L.orc_tape_stat.restype = C.c_long
         L.orc_table_misses.argtypes = [vp]
         L.orc_table_misses.restype = C.c_long
         L.orc_table_hits.argtypes = [vp]
@@ -165,10 +172,15 @@ class Evaluator:
     ``fn(state int8[8,8], player) -> (priors f32[65], value float)`` -- the
     signature of Models.Inference.inference (Models.py:11-31)."""
 
-    def __init__(self, stub=None, fn=None, salt=0, table=None):
+    def __init__(self, stub=None, fn=None, salt=0, table=None, tape=None, slot=0):
         self._keep = []
         self.ctx = None
-        if fn is not None:
+        if tape is not None:  # the slot's recorded evaluation sequence, served in order
+            self.fn_ptr = lib().orc_get_stub(STUB_TAPE)
+            self._cursor = (C.c_void_p * 2)(tape.handle, int(slot))  # {EvalTape*, long slot}
+            self.ctx = C.cast(self._cursor, C.c_void_p)
+            self._keep.append(tape)
+        elif fn is not None:
             def cb(_ctx, s_ptr, player, pri_ptr, val_ptr):
                 s = np.ctypeslib.as_array(s_ptr, shape=(64,)).reshape(8, 8).copy()
                 pri, val = fn(s, int(player))
@@ -221,6 +233,46 @@ class EvalTable:
     def __del__(self):
         try:
             lib().orc_table_free(self.handle)
+        except Exception:
+            pass
+
+
+class EvalTape:
+    """Per-slot sequence of the evaluations an engine consumed (oracle/othello_oracle.c EvalTape): the oracle
+    replaying slot s is served the k-th recorded output on its k-th request and checks that the positions agree."""
+
+    def __init__(self, n_slots, cap_per_slot):
+        self.n_slots = int(n_slots)
+        self.handle = lib().orc_tape_new(self.n_slots, int(cap_per_slot))
+        if not self.handle:
+            raise MemoryError("EvalTape")
+
+    def put_planes(self, planes, mask, priors, values):
+        planes = np.ascontiguousarray(planes, dtype=np.float32).reshape(self.n_slots, 64)
+        mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        priors = np.ascontiguousarray(priors, dtype=np.float32).reshape(self.n_slots, 65)
+        values = np.ascontiguousarray(values, dtype=np.float32).reshape(self.n_slots)
+        rc = lib().orc_tape_put_planes(self.handle, _p(planes), _p(mask), _p(priors), _p(values), self.n_slots)
+        if rc != 0:
+            raise RuntimeError(f"EvalTape.put_planes rc={rc} (tape full?)")
+
+    @property
+    def mismatches(self):
+        return lib().orc_tape_stat(self.handle, 0, 0)
+
+    @property
+    def served(self):
+        return lib().orc_tape_stat(self.handle, 0, 1)
+
+    def recorded(self, slot):
+        return lib().orc_tape_stat(self.handle, slot, 2)
+
+    def consumed(self, slot):
+        return lib().orc_tape_stat(self.handle, slot, 3)
+
+    def __del__(self):
+        try:
+            lib().orc_tape_free(self.handle)
         except Exception:
             pass
 
