@@ -288,6 +288,77 @@ def algorithmic_bytes(d, n_slots, launches, kernel="both"):
     return b
 
 
+def measure_kernel_roofline(eng, run, ev, iters, workload, per_iteration_ms, games_overridden=False):
+    """Roofline block of the MCTS kernels for the pipeline in `run`: an un-graphed pass of `iters` iterations of the same
+    pipeline in which the library records CUDA events around the step kernel and around the move kernel of every launch
+    (othello_b200_experimental.h, per-engine handle), algorithmic bytes from the engine's own counters, the streaming
+    peak from MEASURED_PEAKS.json and the random-access rate measured live."""
+    import ctypes as C
+    import torch
+    from alphazero_othello_b200 import _lib
+    dev, G, lanes = eng.device, eng.n_slots, int(eng.cfg.lanes)
+    torch.cuda.synchronize(dev)
+    c0 = eng.counters()
+    gap_cycles = int(float(os.environ.get("OTH_BENCH_GAP_US", "0")) * 1400)
+    eng.profile_begin(iters)
+    for i in range(iters):
+        if run.fused:  # same launch as in the timed region: softmax / tanh fused into the step kernel
+            lg, vp = ev.raw(eng.nn_input)
+            if gap_cycles:  # experiment: idle gap between the network and the step kernel
+                torch.cuda._sleep(gap_cycles)
+            eng.step_fused(lg, vp)
+        else:
+            ev(eng.nn_input, eng.priors, eng.values)
+            eng.step()
+    kms_seq, mms_seq = eng.profile_end()
+    torch.cuda.synchronize(dev)
+    assert len(kms_seq) == iters
+    c1 = eng.counters()
+    dk = {k: c1[k] - c0[k] for k in c1}
+    if os.environ.get("OTH_BENCH_DUMP_LAUNCHES"):
+        json.dump({"step_ms": kms_seq, "move_ms": mms_seq}, open(os.environ["OTH_BENCH_DUMP_LAUNCHES"], "w"))
+    kms = sorted(kms_seq)
+    k_avg = sum(kms) / len(kms)
+    alg = algorithmic_bytes(dk, G, iters, "step") / iters
+    peak, peak_src = measured_peaks()
+    achieved = alg / (k_avg * 1e-3) / 1e9
+    mms = sorted(mms_seq)
+    m_avg = sum(mms) / len(mms)
+    alg_move = algorithmic_bytes(dk, G, iters, "move") / iters
+    # what HBM delivers for the tree's access pattern: independent random 64-byte reads over a
+    # footprint the size of the arenas (row-activation / TLB bound, far below the streaming copy peak)
+    rnd_gbs, rnd_ms = C.c_double(0), C.c_float(0)
+    foot = min(max(eng.buf_bytes[0] + eng.buf_bytes[1], 1 << 30), 24 << 30)
+    if _lib.lib().oth_host_random_read_probe(foot, 64, C.byref(rnd_gbs), C.byref(rnd_ms)) != 0:
+        rnd_gbs.value = 0.0
+    # dram__bytes_read+write per launch: NOT measured in this run -- taken from the committed `ncu --set full` capture of this config
+    traffic, traffic_src = None, None
+    for tag in ("r02", "r01"):
+        prof = os.path.join(ROOT, "profiles", f"{tag}_mcts_step_{workload}_l{lanes}.json")
+        if os.path.exists(prof) and not games_overridden:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            traffic_src = f"committed ncu capture profiles/{os.path.basename(prof)} (not measured in this run)"
+            break
+    eng.drain(to_host=False)
+    move_kernel = "k_mcts_move_list (due list)" if eng.cfg.move_launch else "k_mcts_move (flag scan)"
+    return {"bound": "hbm", "kernel": f"k_mcts_step{'_fused' if run.fused else ''}<{lanes}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg, "launch_ms_avg": k_avg, "launch_ms_median": kms[len(kms) // 2], "launch_ms_max": kms[-1],
+            "launch_ms_p90": kms[int(len(kms) * 0.9)],
+            "bytes_per_sim": algorithmic_bytes(dk, G, iters) / max(dk["sims"], 1),
+            "random_access": {"peak": rnd_gbs.value, "unit": "GB/s", "frac": achieved / rnd_gbs.value if rnd_gbs.value else None,
+                              "how": f"measured live: independent random 64-byte reads over {foot >> 20} MiB (oth_host_random_read_probe)"},
+            "move_kernel": {"kernel": move_kernel + ": policy target, move sampling, re-rooting copy, game hand-off",
+                            "launch_ms_avg": m_avg, "launch_ms_median": mms[len(mms) // 2], "launch_ms_max": mms[-1],
+                            "note": "runs after every step kernel; in most launches no move is due (median), the copy work sits in "
+                                    "the launch per move where the in-step games all re-root (max)",
+                            "algorithmic_bytes_per_launch": alg_move,
+                            "achieved": alg_move / (m_avg * 1e-3) / 1e9, "frac": alg_move / (m_avg * 1e-3) / 1e9 / peak,
+                            "random_access_frac": alg_move / (m_avg * 1e-3) / 1e9 / rnd_gbs.value if rnd_gbs.value else None},
+            "kernel_share_of_iteration": (k_avg + m_avg) / per_iteration_ms,
+            "event_pair_overhead_note": "each figure includes ~2.7 us that an empty CUDA-event pair measures on this stream"}
+
+
 # -------------------------------------------------------------- B200 arm ----
 def run_b200(a):
     import numpy as np
@@ -451,48 +522,7 @@ def run_b200(a):
     if trace:
         print(f"rank {rank} e2e stages (ms):", [(b[0], round((b[1] - a[1]) * 1e3, 1)) for a, b in zip(trace, trace[1:])], file=sys.stderr)
 
-    # ---- roofline of the MCTS kernels: the library records CUDA events around the step kernel and around the
-    # move kernel of every launch (oth_mcts_profile_create / _read, othello_b200_experimental.h), same pipeline, no graph
-    import ctypes as C
-    torch.cuda.synchronize(dev)
-    c0 = eng.counters()
-    gap_cycles = int(float(os.environ.get("OTH_BENCH_GAP_US", "0")) * 1400)
-    eng.profile_begin(iters)
-    for i in range(iters):
-        if run.fused:  # same launch as in the timed region: softmax / tanh fused into the step kernel
-            lg, vp = ev.raw(eng.nn_input)
-            if gap_cycles:  # experiment: idle gap between the network and the step kernel
-                torch.cuda._sleep(gap_cycles)
-            eng.step_fused(lg, vp)
-        else:
-            ev(eng.nn_input, eng.priors, eng.values)
-            eng.step()
-    kms_seq, mms_seq = eng.profile_end()
-    torch.cuda.synchronize(dev)
-    assert len(kms_seq) == iters
-    c1 = eng.counters()
-    dk = {k: c1[k] - c0[k] for k in c1}
-    if os.environ.get("OTH_BENCH_DUMP_LAUNCHES"):
-        json.dump({"step_ms": kms_seq, "move_ms": mms_seq}, open(os.environ["OTH_BENCH_DUMP_LAUNCHES"], "w"))
-    kms = sorted(kms_seq)
-    k_avg = sum(kms) / len(kms)
-    alg = algorithmic_bytes(dk, G, iters, "step") / iters
-    peak, peak_src = measured_peaks()
-    achieved = alg / (k_avg * 1e-3) / 1e9
-    mms = sorted(mms_seq)
-    m_avg = sum(mms) / len(mms)
-    alg_move = algorithmic_bytes(dk, G, iters, "move") / iters
-    # what HBM delivers for the tree's access pattern: independent random 64-byte reads over a
-    # footprint the size of the arenas (row-activation / TLB bound, far below the streaming copy peak)
-    rnd_gbs, rnd_ms = C.c_double(0), C.c_float(0)
-    foot = min(max(eng.buf_bytes[0] + eng.buf_bytes[1], 1 << 30), 24 << 30)
-    if _lib.lib().oth_host_random_read_probe(foot, 64, C.byref(rnd_gbs), C.byref(rnd_ms)) != 0:
-        rnd_gbs.value = 0.0
-    traffic = None  # dram__bytes_read+write per launch from the committed `ncu --set full` capture of this config
-    prof = os.path.join(ROOT, "profiles", f"r01_mcts_step_{a.workload}_l{a.lanes}.json")
-    if os.path.exists(prof) and not a.games:
-        traffic = json.load(open(prof)).get("dram_bytes_per_launch")
-    eng.drain(to_host=False)
+    roof = measure_kernel_roofline(eng, run, ev, iters, a.workload, per_iteration_ms=ms / a.steps / iters, games_overridden=bool(a.games))
 
     from alphazero_othello_b200 import _cudnn_fused
     fused_plans = _cudnn_fused.chosen_plans()
@@ -524,20 +554,7 @@ def run_b200(a):
             # counted as one per iteration all the same, an upper bound)
             "gpu_launches": a.steps * iters * (3 + (0 if fused_plans else (5 if kind == "big" else 1))),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": f"k_mcts_step{'_fused' if run.fused else ''}<{a.lanes}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg, "launch_ms_avg": k_avg, "launch_ms_median": kms[len(kms) // 2], "launch_ms_max": kms[-1],
-                         "launch_ms_p90": kms[int(len(kms) * 0.9)],
-                         "bytes_per_sim": algorithmic_bytes(dk, G, iters) / max(dk["sims"], 1),
-                         "random_access": {"peak": rnd_gbs.value, "unit": "GB/s", "frac": achieved / rnd_gbs.value if rnd_gbs.value else None,
-                                           "how": f"measured live: independent random 64-byte reads over {foot >> 20} MiB (oth_host_random_read_probe)"},
-                         "move_kernel": {"kernel": "k_mcts_move (policy target, move sampling, re-rooting copy, game hand-off)",
-                                         "launch_ms_avg": m_avg, "launch_ms_median": mms[len(mms) // 2], "launch_ms_max": mms[-1],
-                                         "note": "runs after every step kernel; most launches only scan the per-slot move flags "
-                                                 "(median), the copy work sits in the launch per move where the in-step games all re-root (max)",
-                                         "algorithmic_bytes_per_launch": alg_move,
-                                         "achieved": alg_move / (m_avg * 1e-3) / 1e9, "frac": alg_move / (m_avg * 1e-3) / 1e9 / peak},
-                         "kernel_share_of_iteration": (k_avg + m_avg) / (ms / a.steps / iters)},
+            "roofline": roof,
             # the step's dominant cost is the (library) network: its share of the dense bf16 peak sustained by cuBLAS on this pool
             "network_roofline": network_roofline(kind, evals_total / (ms * 1e-3), world),
             "search_counters_per_step": {k: d[k] / a.steps for k in ("sims", "evals", "terminal_sims", "moves", "games", "nodes", "copied", "levels", "children")},
@@ -552,34 +569,77 @@ def run_b200(a):
     return out, dev
 
 
-def aux_selfplay_rate(dev, workload, steps=8, warm=3):
+def aux_selfplay_rate(dev, workload, steps=8, warm=3, dtype=None, tf32=False, iters=None, with_roofline=False):
     """Resident self-play throughput of another BASELINE config on the same GPU (same pipeline as the
-    headline: network twin + oth_mcts_step_fused replayed as a CUDA graph; a step = sims/move iterations)."""
+    headline: network twin + oth_mcts_step_fused replayed as a CUDA graph; a step = sims/move iterations).
+    dtype torch.float32 (+ tf32) runs the float32 twin of the network: the same-precision comparator of the headline."""
     import torch
     from alphazero_othello_b200 import _lib
     from alphazero_othello_b200.Models import fold_for_inference
     from alphazero_othello_b200.engine import BatchedPolicy, MctsEngine, SelfPlayRunner
     desc, kind, G, sims = WORKLOADS[workload]
+    iters = iters or sims
     args = dict(TRAIN_ARGS, num_simulations=sims)
-    eng = MctsEngine(G, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=-1, device=dev,
-                     out_pos_cap=G * 80, out_game_cap=G + 64)
-    run = SelfPlayRunner(eng, BatchedPolicy(fold_for_inference(make_net(kind).to(dev), torch.bfloat16), dev, torch.float32))
-    run.warm_start()
-    for _ in range(warm):
-        run.run_iterations(sims)
-    torch.cuda.synchronize(dev)
-    c0 = eng.counters()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        run.run_iterations(sims)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    c1 = eng.counters()
-    eng.raise_on_error()
-    ms = e0.elapsed_time(e1)
-    return {"workload": f"{workload}: {desc}", "net": kind, "sims_per_s": (c1["sims"] - c0["sims"]) / (ms * 1e-3),
-            "positions_per_s": (c1["moves"] - c0["moves"]) / (ms * 1e-3), "steps": steps, "warmup": warm, "ms_per_step": ms / steps}
+    dtype = dtype or torch.bfloat16
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    if dtype == torch.float32:
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+    try:
+        eng = MctsEngine(G, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=-1, device=dev,
+                         out_pos_cap=G * 80 + 4096, out_game_cap=G + 64)
+        ev = BatchedPolicy(fold_for_inference(make_net(kind).to(dev), dtype), dev, torch.float32)
+        run = SelfPlayRunner(eng, ev)
+        run.warm_start()
+        for _ in range(warm):
+            run.run_iterations(iters)
+        torch.cuda.synchronize(dev)
+        c0 = eng.counters()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            run.run_iterations(iters)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        c1 = eng.counters()
+        eng.raise_on_error()
+        ms = e0.elapsed_time(e1)
+        sims_s = (c1["sims"] - c0["sims"]) / (ms * 1e-3)
+        out = {"workload": f"{workload}: {desc}", "net": kind, "network_dtype": str(dtype).replace("torch.", "") + ("+tf32" if dtype == torch.float32 and tf32 else ""),
+               "sims_per_s": sims_s, "positions_per_s": (c1["moves"] - c0["moves"]) / (ms * 1e-3), "steps": steps, "warmup": warm,
+               "iters_per_step": iters, "ms_per_step": ms / steps, "lanes": int(eng.cfg.lanes),
+               "network_roofline": network_roofline(kind, (c1["evals"] - c0["evals"]) / (ms * 1e-3)) if dtype == torch.bfloat16 else None}
+        if with_roofline:
+            out["roofline"] = measure_kernel_roofline(eng, run, ev, min(iters, 200), workload, per_iteration_ms=ms / steps / iters)
+        return out
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def aux_one_self_play(dev):
+    """Config C2 through the drop-in surface: ``one_self_play((8, args, (class, config, state_dict), None))`` exactly as
+    train.py:199-225 calls the reference's worker -- one whole game, 100 simulations per move, the float32 small network
+    evaluated on the GPU at batch 1 by the drop-in MCTS class (one CUDA-graph replay per simulation)."""
+    import numpy as np
+    import torch
+    from alphazero_othello_b200.Models import FastOthelloNet
+    from alphazero_othello_b200.self_play_worker import one_self_play
+    desc, kind, G, sims = WORKLOADS["c2"]
+    args = dict(TRAIN_ARGS, num_simulations=sims)
+    torch.manual_seed(0)
+    net = FastOthelloNet(8, 65).eval()
+    state = (FastOthelloNet, net.get_config(), net.state_dict())
+    best = None
+    for rep in range(2):
+        np.random.seed(rep)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        traj = one_self_play((8, args, state, None))
+        dt = time.perf_counter() - t0
+        if best is None or dt / len(traj) < best[0] / best[1]:
+            best = (dt, len(traj))
+    return {"workload": f"c2: {desc} -- through the drop-in one_self_play (host loop over the GPU tree, float32 network, whole game, "
+                        "engine construction and graph capture included)",
+            "seconds": best[0], "plies": best[1], "sims_per_s": best[1] * sims / best[0], "positions_per_s": best[1] / best[0]}
 
 
 def aux_public_api(dev, workload="c3"):
@@ -657,17 +717,24 @@ def aux_env(dev):
     _lib.check(_lib.lib().oth_host_rollout(9, 0, n, sc.ctypes.data, pl.ctypes.data, None, 0, None, None, C.byref(tot), C.byref(k2)))
     t1 = time.perf_counter()
     steps_s = best[1] / (best[0] * 1e-3)
-    ncu = {}
+    # instructions per ply and the ALU-pipe utilisation are NOT measured in this run: they come from the committed
+    # `ncu --set full` capture of the same kernel and size (the survey's estimate was 600 instructions per ply)
+    instr, ncu = 600.0, {"instr_per_ply_source": "SURVEY 8(d) estimate"}
     prof = os.path.join(ROOT, "profiles", "r01_rollout_c1.json")
-    if os.path.exists(prof):  # committed `ncu --set full` capture of the same kernel and size
+    if os.path.exists(prof):
         pj = json.load(open(prof))
-        ncu = {"alu_pipe_pct_of_peak_ncu": pj["alu_pipe_pct_of_peak"], "thread_instructions_per_ply_ncu": pj["thread_instructions_per_ply"]}
+        instr = float(pj["thread_instructions_per_ply"])
+        ncu = {"instr_per_ply_source": "committed ncu capture profiles/r01_rollout_c1.json (smsp__inst_executed x threads / plies)",
+               "alu_pipe_frac": pj["alu_pipe_pct_of_peak"] / 100.0,
+               "alu_pipe_frac_source": "committed ncu capture profiles/r01_rollout_c1.json "
+                                       "(sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active; the kernel's binding pipe)"}
     return {"workload": "c1: Othello 8x8 random-policy rollouts, 2^22 games", "env_steps_per_s": steps_s, "kernel_ms": best[0],
             "plies": best[1], "e2e_env_steps_per_s": tot.value / (t1 - t0), "e2e_d2h_bytes": n * 8,
-            "int32_roofline": {"bound": "int32-alu", "instr_per_ply": 600, "achieved_ginstr_s": steps_s * 600 / 1e9,
-                               "peak_ginstr_s": ips.value / 1e9, "frac": steps_s * 600 / ips.value,
-                               "peak_source": "measured live: LOP3+IADD3 probe kernel (oth_host_int32_peak; it issues to the ALU and FMA pipes, "
-                                              "k_rollout's shift/logic mix can only use the ALU pipe)", **ncu}}
+            "int32_roofline": {"bound": "int32-alu", "instr_per_ply": instr, "achieved_ginstr_s": steps_s * instr / 1e9,
+                               "mixed_pipe_probe_peak_ginstr_s": ips.value / 1e9, "frac_of_mixed_pipe_probe": steps_s * instr / ips.value,
+                               "mixed_pipe_probe": "measured live: LOP3+IADD3 probe kernel (oth_host_int32_peak); it issues to the ALU AND "
+                                                   "FMA pipes, which k_rollout's shift/logic mix cannot -- an upper bound no shift-heavy kernel reaches",
+                               **ncu}}
 
 
 def aux_env_step_api(dev):
@@ -710,35 +777,50 @@ def aux_env_step_api(dev):
     return out
 
 
-def aux_search_only(dev, G, sims, lanes):
-    """Search-only variant: the same kernel with the device hash-stub evaluator, so a
-    launch runs whole simulations back to back without the network in between."""
+def aux_search_only(dev, G, sims):
+    """Search-only variant through the PRODUCTION kernel pair: the step kernel with the device hash stub in
+    the network's place (cfg.split_stub) + the move kernel, back to back -- exactly one evaluation per slot per launch,
+    as behind the network, but with nothing in between."""
+    import ctypes as C
     import torch
     from alphazero_othello_b200 import _lib
     from alphazero_othello_b200.engine import MctsEngine
     args = dict(TRAIN_ARGS, num_simulations=sims)
-    eng = MctsEngine(G, args, self_play=True, eval_kind=_lib.EVAL_STUB_H, games_per_slot=-1, device=dev, lanes=lanes,
-                     max_inline_sims=16, out_pos_cap=G * 80, out_game_cap=G + 64, stub_salt=1)
+    eng = MctsEngine(G, args, self_play=True, eval_kind=_lib.EVAL_STUB_H, games_per_slot=-1, device=dev, split_stub=True,
+                     out_pos_cap=G * 80 + 4096, out_game_cap=G + 64, stub_salt=1)
     eng.reset()
-    for _ in range(30):
+    for _ in range(sims + sims // 2):  # into the second move: trees with re-used subtrees
         eng.step()
     eng.drain(to_host=False)
+    torch.cuda.synchronize(dev)
     c0 = eng.counters()
+    n = min(sims, 200)
+    eng.profile_begin(n)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    n = 60
     for _ in range(n):
         eng.step()
     e1.record()
     torch.cuda.synchronize(dev)
+    kms, mms = eng.profile_end()
     c1 = eng.counters()
     ms = e0.elapsed_time(e1)
     d = {k: c1[k] - c0[k] for k in c1}
     eng.raise_on_error()
     peak, _ = measured_peaks()
-    gbs = algorithmic_bytes(dict(d, evals=0), G, n) / (ms * 1e-3) / 1e9  # no network I/O in this variant
-    return {"workload": f"search-only: {G} games, {sims} sims/move, device stub evaluator, 16 simulations per slot per launch",
-            "sims_per_s": d["sims"] / (ms * 1e-3), "launch_ms": ms / n, "hbm_gbs": gbs, "hbm_frac": gbs / peak}
+    rnd_gbs, rnd_ms = C.c_double(0), C.c_float(0)
+    foot = min(max(eng.buf_bytes[0] + eng.buf_bytes[1], 1 << 30), 24 << 30)
+    if _lib.lib().oth_host_random_read_probe(foot, 64, C.byref(rnd_gbs), C.byref(rnd_ms)) != 0:
+        rnd_gbs.value = 0.0
+    k_avg = sum(kms) / len(kms)
+    alg_step = algorithmic_bytes(dict(d, evals=0), G, n, "step") + d["evals"] * (16 + 16 + 32 + 8)  # no network I/O in this variant
+    gbs = alg_step / n / (k_avg * 1e-3) / 1e9
+    return {"workload": f"search-only: {G} games, {sims} sims/move, k_mcts_step_devstub<{int(eng.cfg.lanes)}> + move kernel, "
+                        "one evaluation per slot per launch",
+            "sims_per_s": d["sims"] / (ms * 1e-3), "sims_per_s_step_kernel_alone": d["sims"] / n / (k_avg * 1e-3),
+            "launch_ms_step_avg": k_avg, "launch_ms_move_avg": sum(mms) / len(mms), "launch_ms_move_max": max(mms),
+            "hbm_gbs": gbs, "hbm_frac": gbs / peak, "random_access_gbs": rnd_gbs.value,
+            "random_access_frac": gbs / rnd_gbs.value if rnd_gbs.value else None}
 
 
 def main():
@@ -800,10 +882,18 @@ def main():
     if rank == 0:
         if world == 1 and not a.no_aux:
             out["aux"] = aux_env(dev)
-            out["aux"]["search_only"] = aux_search_only(dev, out["config"]["games_per_gpu"], sims, a.lanes)
+            import torch
+            out["aux"]["search_only"] = aux_search_only(dev, out["config"]["games_per_gpu"], sims)
             out["aux"]["env_step_api"] = aux_env_step_api(dev)
-            other = "c3" if a.workload != "c3" else "c4"  # north_star: both architectures
-            out["aux"]["other_architecture"] = aux_selfplay_rate(dev, other)
+            other = "c3" if a.workload != "c3" else "c4"  # north_star: both architectures, every BASELINE config
+            out["aux"]["other_architecture"] = aux_selfplay_rate(dev, other, with_roofline=True)
+            if a.workload != "c2":
+                out["aux"]["c2_one_game"] = aux_selfplay_rate(dev, "c2", steps=12, warm=3, with_roofline=True)
+            out["aux"]["c2_one_self_play_dropin"] = aux_one_self_play(dev)
+            # same-precision comparator of the headline: the float32 twin of the same network (TF32 tensor cores, and plain FP32)
+            out["aux"]["network_precision"] = {
+                "tf32": aux_selfplay_rate(dev, a.workload, steps=2, warm=1, dtype=torch.float32, tf32=True, iters=40),
+                "fp32": aux_selfplay_rate(dev, a.workload, steps=1, warm=1, dtype=torch.float32, tf32=False, iters=10)}
             out["aux"]["public_api_whole_games"] = aux_public_api(dev, "c3")
             import oracle
             oracle.build()
