@@ -165,9 +165,13 @@ class _StemGemm(nn.Module):
 
     def forward(self, x):  # x [B,1,8,8]: float32 (engine path) or already in the compute dtype
         B = x.size(0)
-        cols = getattr(self, "_cols", None)
-        if cols is None or cols.size(0) != B or cols.dtype != self.wt.dtype or cols.device != x.device:
-            cols = self._cols = torch.zeros(B, 8, 8, 16, dtype=self.wt.dtype, device=x.device)  # K columns 9..15 stay zero
+        # one im2col buffer PER batch size, kept for the life of the module: CUDA graphs captured at different batch
+        # sizes (evaluation de-duplication buckets) each hold the address of theirs
+        cache = self.__dict__.setdefault("_cols", {})
+        key = (B, self.wt.dtype, x.device)
+        cols = cache.get(key)
+        if cols is None:
+            cols = cache[key] = torch.zeros(B, 8, 8, 16, dtype=self.wt.dtype, device=x.device)  # K columns 9..15 stay zero
         if x.dtype == torch.float32 and cols.dtype == torch.bfloat16 and x.is_contiguous():
             import ctypes as C
             from . import _lib

@@ -99,6 +99,11 @@ _SIGS = {
     "oth_mcts_step": (C.c_int, [C.c_void_p] * 6),
     "oth_mcts_step_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "oth_mcts_step_fused_mapped": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "oth_mcts_dedup_workspace_bytes": (C.c_int, [C.c_int32, C.c_void_p]),
+    "oth_mcts_dedup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
     "oth_mcts_advance": (C.c_int, [C.c_void_p] * 4),
     "oth_mcts_poll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "oth_mcts_profile_create": (C.c_int, [C.c_int32, C.c_void_p]),

@@ -129,6 +129,7 @@ struct Params {
     const void* logits;
     const void* vpre;
     int logits_stride, vpre_stride, raw_bf16;
+    const int* eval_map;  // optional (evaluation de-duplication): row of logits / vpre that holds slot s's evaluation, -1 = none this launch
     float* priors_out;  // optional: the softmax / tanh the kernel applied, for record & replay
     float* values_out;
     float* nn_input;
@@ -1033,24 +1034,27 @@ struct Ctx {
         constexpr bool stub = STUB;
         float pv[NPL];
         float nn_value = 0.0f;
+        int eval_row = slot;
         if (!stub && !DEVSTUB && !(MOVE && !STUB)) {
             if constexpr (FUSED) {
+                if (P.eval_map) eval_row = P.eval_map[slot];
+                const size_t row = (size_t)(eval_row < 0 ? 0 : eval_row);  // a slot without a row reads row 0 and discards it
                 if (P.raw_bf16) {
-                    const __nv_bfloat16* lg = (const __nv_bfloat16*)P.logits + (size_t)slot * P.logits_stride;
+                    const __nv_bfloat16* lg = (const __nv_bfloat16*)P.logits + row * P.logits_stride;
 #pragma unroll
                     for (int k = 0; k < NPL; k++) {
                         const int a = lane + k * LANES;
                         pv[k] = a < OTH_NUM_ACTIONS ? __bfloat162float(lg[a]) : -INFINITY;
                     }
-                    nn_value = __bfloat162float(((const __nv_bfloat16*)P.vpre)[(size_t)slot * P.vpre_stride]);
+                    nn_value = __bfloat162float(((const __nv_bfloat16*)P.vpre)[row * P.vpre_stride]);
                 } else {
-                    const float* lg = (const float*)P.logits + (size_t)slot * P.logits_stride;
+                    const float* lg = (const float*)P.logits + row * P.logits_stride;
 #pragma unroll
                     for (int k = 0; k < NPL; k++) {
                         const int a = lane + k * LANES;
                         pv[k] = a < OTH_NUM_ACTIONS ? lg[a] : -INFINITY;
                     }
-                    nn_value = ((const float*)P.vpre)[(size_t)slot * P.vpre_stride];
+                    nn_value = ((const float*)P.vpre)[row * P.vpre_stride];
                 }
             } else {
                 const float* pr = P.priors + (size_t)slot * OTH_NUM_ACTIONS;
@@ -1066,6 +1070,7 @@ struct Ctx {
         load_hot_head();
         c = P.ctl[slot];
         if (c.top < 1) return;  // slot never given a tree (zero-filled control block): nothing to do
+        if (FUSED && eval_row < 0 && c.phase == OTH_PH_WAIT_EVAL) return;  // its position did not fit this launch's bucket: it waits
         bind_arena();
         gsync();
         if (c.phase == OTH_PH_WAIT_EVAL || c.phase == OTH_PH_RUN) {
@@ -1579,6 +1584,7 @@ int make_params(const oth_mcts_config* cfg, const oth_mcts_buffers* b, Params* p
     p->logits = nullptr;
     p->vpre = nullptr;
     p->logits_stride = p->vpre_stride = p->raw_bf16 = 0;
+    p->eval_map = nullptr;
     p->priors_out = nullptr;
     p->values_out = nullptr;
     p->nn_input = nullptr;
@@ -1799,6 +1805,14 @@ extern "C" int oth_mcts_step_fused(const oth_mcts_config* cfg, const oth_mcts_bu
                                    const void* value_preact, int64_t value_stride, int32_t is_bf16, float* priors_out, float* values_out,
                                    float* nn_input, void* stream)
 {
+    return oth_mcts_step_fused_mapped(cfg, b, logits, logits_stride, value_preact, value_stride, is_bf16, nullptr, priors_out, values_out,
+                                      nn_input, stream);
+}
+
+extern "C" int oth_mcts_step_fused_mapped(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const void* logits, int64_t logits_stride,
+                                          const void* value_preact, int64_t value_stride, int32_t is_bf16, const int32_t* eval_map,
+                                          float* priors_out, float* values_out, float* nn_input, void* stream)
+{
     Params p;
     const int rc = make_params(cfg, b, &p);
     if (rc != OTH_OK) return rc;
@@ -1810,6 +1824,7 @@ extern "C" int oth_mcts_step_fused(const oth_mcts_config* cfg, const oth_mcts_bu
     p.logits_stride = (int)logits_stride;
     p.vpre_stride = (int)value_stride;
     p.raw_bf16 = is_bf16 ? 1 : 0;
+    p.eval_map = eval_map;
     p.priors_out = priors_out;
     p.values_out = values_out;
     p.nn_input = nn_input;

@@ -154,15 +154,23 @@ class MctsEngine:
                    self._stream())
         self.launches += 1
 
-    def step_fused(self, logits, value_preact, record=False):
+    def dedup(self, bucket, compact_input, eval_map, stats, workspace):
+        """oth_mcts_dedup: distinct pending leaves -> compact_input [bucket,1,8,8] + eval_map int32[n_slots]; stats int32[2]."""
+        self._call(self.L.oth_mcts_dedup, int(bucket), workspace.data_ptr(), workspace.numel(),
+                   None if compact_input is None else compact_input.data_ptr(), None if eval_map is None else eval_map.data_ptr(),
+                   stats.data_ptr(), self._stream())
+
+    def step_fused(self, logits, value_preact, record=False, eval_map=None):
         """``step`` with the network's softmax / tanh applied in-kernel: ``logits`` [n_slots, >=65] and
         ``value_preact`` [n_slots, >=1] are (possibly strided) float32 or bfloat16 views of the head outputs.
         ``record=True`` writes the priors / values the kernel used to ``self.priors`` / ``self.values``."""
         assert logits.dtype == value_preact.dtype and logits.dtype in (torch.float32, torch.bfloat16)
-        assert logits.stride(1) == 1 and logits.size(0) == self.n_slots and value_preact.size(0) == self.n_slots
-        self._call(self.L.oth_mcts_step_fused, logits.data_ptr(), logits.stride(0), value_preact.data_ptr(), value_preact.stride(0),
-                   1 if logits.dtype == torch.bfloat16 else 0, self.priors.data_ptr() if record else None,
-                   self.values.data_ptr() if record else None, self.nn_input.data_ptr(), self._stream())
+        assert logits.stride(1) == 1 and logits.size(0) == value_preact.size(0)
+        assert eval_map is not None or logits.size(0) == self.n_slots  # de-duplicated batches are indexed through eval_map
+        self._call(self.L.oth_mcts_step_fused_mapped, logits.data_ptr(), logits.stride(0), value_preact.data_ptr(), value_preact.stride(0),
+                   1 if logits.dtype == torch.bfloat16 else 0, None if eval_map is None else eval_map.data_ptr(),
+                   self.priors.data_ptr() if record else None, self.values.data_ptr() if record else None, self.nn_input.data_ptr(),
+                   self._stream())
         self.launches += 1
 
     # per-launch timing of the step / move kernels (othello_b200_experimental.h), per engine
@@ -291,9 +299,19 @@ class BatchedPolicy:
 
 class SelfPlayRunner:
     """Batched replacement of ``Trainer.collect_self_play_games`` (train.py:199-225):
-    plays ``n_slots`` concurrent games with one network evaluation per simulation per game."""
+    plays ``n_slots`` concurrent games with one network evaluation per simulation per game.
 
-    def __init__(self, engine, evaluator=None, use_graph=True, fused=True, record=False):
+    ``dedup``: evaluation de-duplication (oth_mcts_dedup).  Games that start from the same position ask for the same
+    leaves during their first plies; with it the network runs on the DISTINCT pending positions of a batch, padded to
+    the next of a few bucket sizes (n/2, n/4, ... each captured as its own CUDA graph), and the step kernel reads every
+    slot's outputs through an index map.  The bucket is chosen on the host from the distinct-position count the device
+    reported a few iterations earlier; positions that do not fit a too-small bucket just wait one launch, so the choice
+    only affects speed.  "auto" enables it for the fused pipeline from 8192 slots up (measured: at 4096 slots of the
+    small network a half-size batch costs 2/3 of a full one and the compaction pass eats the rest)."""
+
+    DEDUP_BLOCK = 16  # iterations per host decision (and per throttling event)
+
+    def __init__(self, engine, evaluator=None, use_graph=True, fused=True, record=False, dedup=False):
         """``record=True``: every launch also writes the priors / values it consumed to ``engine.priors`` /
         ``engine.values`` (fused path: what the kernel's own softmax / tanh produced), so a checker can replay them."""
         self.e = engine
@@ -309,6 +327,30 @@ class SelfPlayRunner:
         self.graph = None
         # network twins hand the kernel raw logits: softmax / tanh are fused into oth_mcts_step_fused
         self.fused = fused and self.external and getattr(evaluator, "raw", None) is not None and evaluator.has_raw
+        if dedup == "auto":  # pays where the network's time is linear in the batch: large batches of the large network
+            dedup = self.fused and engine.n_slots >= 8192 and os.environ.get("OTH_DEDUP", "1") != "0"
+        self.dedup = bool(dedup) and self.fused
+        self.last_map = None        # eval_map of the iteration being executed (None: every waiting slot is served)
+        self.rows_evaluated = 0     # network rows computed so far (== n_slots per iteration without de-duplication)
+        self.force_bucket = None    # test knob: always use this bucket, however many distinct positions there are
+        if self.dedup:
+            n, dev = engine.n_slots, engine.device
+            self.buckets = []
+            b = n // 2
+            while b >= max(256, n // 32):
+                self.buckets.append(b)
+                b //= 2
+            nb = C.c_int64(0)
+            _lib.check(engine.L.oth_mcts_dedup_workspace_bytes(n, C.byref(nb)), "oth_mcts_dedup_workspace_bytes")
+            self._ws = torch.zeros(nb.value, dtype=torch.uint8, device=dev)
+            self._map = torch.full((n,), -1, dtype=torch.int32, device=dev)
+            self._stats = torch.zeros(2, dtype=torch.int32, device=dev)
+            self._stats_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+            self._compact = {b: torch.zeros((b, 1, 8, 8), dtype=torch.float32, device=dev) for b in self.buckets}
+            self._graphs = {}      # bucket (0 = whole batch + count) -> CUDA graph
+            self._events = []      # throttle: the host stays at most two blocks ahead of the device
+            self._recent = [n, n]  # distinct-position counts last reported by the device
+            self.bucket_iterations = {0: 0, **{b: 0 for b in self.buckets}}
 
     def _iteration(self):
         if self.external and self.fused:
@@ -319,6 +361,21 @@ class SelfPlayRunner:
             self.evaluator(self.e.nn_input, self.e.priors, self.e.values)
         self.e.step()
 
+    def _dedup_iteration(self, bucket):
+        """bucket = 0: the whole batch as usual, plus a count of its distinct positions (the host's next decision);
+        otherwise: compact the distinct positions into ``bucket`` rows, evaluate those, map the outputs back."""
+        e = self.e
+        if bucket == 0:
+            e.dedup(0, None, None, self._stats, self._ws)
+            self._stats_host.copy_(self._stats, non_blocking=True)
+            self._iteration()
+            return
+        x = self._compact[bucket]
+        e.dedup(bucket, x, self._map, self._stats, self._ws)
+        self._stats_host.copy_(self._stats, non_blocking=True)
+        logits, v = self.evaluator.raw(x)
+        e.step_fused(logits, v, record=self.record, eval_map=self._map)
+
     def warm_start(self):
         self.e.reset()
         if self.external:
@@ -326,18 +383,19 @@ class SelfPlayRunner:
             self.e.values.zero_()
         self.e.step()  # emits the root leaves
 
-    def _capture(self):
+    def _capture(self, fn=None):
+        fn = fn or self._iteration
         dev = self.e.device
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(s):
             for _ in range(2):  # executed (they are real iterations), so lazy initialisation is done before capture
-                self._hooked(self._iteration)
+                self._hooked(fn)
         torch.cuda.current_stream(dev).wait_stream(s)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._iteration()  # recorded, not executed
-        self.graph = g
+            fn()  # recorded, not executed
+        return g
 
     def _hooked(self, fn):
         if self.before_iteration is not None:
@@ -346,17 +404,69 @@ class SelfPlayRunner:
         if self.after_iteration is not None:
             self.after_iteration()
 
+    def _choose_bucket(self):
+        """Smallest bucket that holds the distinct positions seen lately with a quarter to spare (the count grows while
+        the trees of a move diverge); 0 = evaluate the whole batch."""
+        if self.force_bucket is not None:
+            return self.force_bucket
+        need = max(self._recent) * 5 // 4 + 64
+        fit = [b for b in self.buckets if b >= need]
+        return min(fit) if fit else 0
+
+    def _dedup_graph(self, b):
+        """The CUDA graph of one iteration variant: b = None plain, 0 whole batch + count, else compacted to b rows.
+        Capturing executes two real iterations of that variant first (lazy initialisation, cuDNN plan selection)."""
+        key = "plain" if b is None else b
+        g = self._graphs.get(key)
+        if g is None:
+            self.last_map = self._map if b else None
+            g = self._graphs[key] = self._capture((lambda: self._dedup_iteration(b)) if b is not None else self._iteration)
+            self.rows_evaluated += 2 * (b or self.e.n_slots)
+            self.e.launches += 2
+        return g
+
+    def _run_dedup(self, n):
+        if self.use_graph and not self._graphs:  # every variant is captured up front, not in the middle of a run
+            for b in [None, 0] + self.buckets:
+                self._dedup_graph(b)
+        done = 0
+        while done < n:
+            k = min(self.DEDUP_BLOCK, n - done)
+            if len(self._events) >= 2:  # wait for the block before the previous one: its counts are on the host now
+                self._events.pop(0).synchronize()
+            self._recent = [self._recent[1], int(self._stats_host[0])]
+            bucket = self._choose_bucket()
+            for i in range(k):
+                b = bucket if (bucket or i == 0) else None  # whole-batch mode: count once per block, then the plain graph
+                self.last_map = self._map if b else None
+                self.rows_evaluated += b or self.e.n_slots
+                if not self.use_graph:
+                    self._hooked((lambda: self._dedup_iteration(b)) if b is not None else self._iteration)
+                else:
+                    self._hooked(self._dedup_graph(b).replay)
+                self.e.launches += 1
+                self.bucket_iterations[bucket] += 1
+            ev = torch.cuda.Event()
+            ev.record()
+            self._events.append(ev)
+            done += k
+
     def run_iterations(self, n):
         """n x (network forward over the leaf batch + one fused MCTS kernel launch), as CUDA-graph replays."""
-        if self.use_graph and self.graph is None:
-            self._capture()
         torch.cuda.nvtx.range_push(f"selfplay:{n} iterations (network + oth_mcts_step)")
+        if self.dedup:
+            self._run_dedup(n)
+            torch.cuda.nvtx.range_pop()
+            return
+        if self.use_graph and self.graph is None:
+            self.graph = self._capture()
         for _ in range(n):
             if self.graph is not None:
                 self._hooked(self.graph.replay)
                 self.e.launches += 1
             else:
                 self._hooked(self._iteration)
+        self.rows_evaluated += n * self.e.n_slots
         torch.cuda.nvtx.range_pop()
 
     def play(self, check_every=64, max_iterations=None):

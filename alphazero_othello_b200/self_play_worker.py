@@ -75,7 +75,7 @@ def one_self_play(args_tuple):
 
 
 def collect_self_play_games(policy, args, n_games, *, n_slots=None, device="cuda:0", dtype=torch.bfloat16, seed=0,
-                            game_id_base=0, fold=True, use_graph=True, return_raw=False):
+                            game_id_base=0, fold=True, use_graph=True, return_raw=False, dedup="auto"):
     """Play ``n_games`` self-play games with ``policy`` (a torch module) on one GPU."""
     from .Models import fold_for_inference
     n_slots = int(n_slots or min(n_games, 4096))
@@ -88,7 +88,7 @@ def collect_self_play_games(policy, args, n_games, *, n_slots=None, device="cuda
         ev = BatchedPolicy(net, device, torch.float32)
     else:
         ev = BatchedPolicy(net, device, dtype)
-    out = SelfPlayRunner(eng, ev, use_graph=use_graph).play()
+    out = SelfPlayRunner(eng, ev, use_graph=use_graph, dedup=dedup).play()
     eng.raise_on_error()
     return out if return_raw else split_games(out)[:n_games]
 
@@ -110,7 +110,7 @@ def collect_self_play_games_distributed(policy, args, n_games_per_rank, *, n_slo
     base, stride = parallel.shard_game_ids(rank, world, n_slots)
     eng = MctsEngine(n_slots, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=gps, device=dev, seed=seed,
                      game_id_base=base, game_id_stride=stride)
-    out = SelfPlayRunner(eng, BatchedPolicy(fold_for_inference(net, dtype), dev, torch.float32)).play()
+    out = SelfPlayRunner(eng, BatchedPolicy(fold_for_inference(net, dtype), dev, torch.float32), dedup="auto").play()
     eng.raise_on_error()
     merged = parallel.gather_replay({k: v.to(dev) for k, v in out.items() if k != "states"}, dst=0, device=dev)
     if merged is None:

@@ -340,6 +340,12 @@ def measure_kernel_roofline(eng, run, ev, iters, workload, per_iteration_ms, gam
             traffic_src = f"committed ncu capture profiles/{os.path.basename(prof)} (not measured in this run)"
             break
     eng.drain(to_host=False)
+    # what a CUDA-event pair with NOTHING between them reads on this stream: part of every per-launch figure above
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(65)]
+    for e in evs:
+        e.record()
+    torch.cuda.synchronize(dev)
+    ovh = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(64))[32]
     move_kernel = "k_mcts_move_list (due list)" if eng.cfg.move_launch else "k_mcts_move (flag scan)"
     return {"bound": "hbm", "kernel": f"k_mcts_step{'_fused' if run.fused else ''}<{lanes}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -356,7 +362,10 @@ def measure_kernel_roofline(eng, run, ev, iters, workload, per_iteration_ms, gam
                             "achieved": alg_move / (m_avg * 1e-3) / 1e9, "frac": alg_move / (m_avg * 1e-3) / 1e9 / peak,
                             "random_access_frac": alg_move / (m_avg * 1e-3) / 1e9 / rnd_gbs.value if rnd_gbs.value else None},
             "kernel_share_of_iteration": (k_avg + m_avg) / per_iteration_ms,
-            "event_pair_overhead_note": "each figure includes ~2.7 us that an empty CUDA-event pair measures on this stream"}
+            "event_pair_overhead_ms": ovh,
+            "kernel_share_of_iteration_net_of_event_overhead": max(k_avg + m_avg - 2 * ovh, 0.0) / per_iteration_ms,
+            "event_pair_overhead_note": "an empty CUDA-event pair on this stream reads event_pair_overhead_ms (measured live, median of "
+                                        "64); every per-launch figure above includes it once, kernel_share_of_iteration twice"}
 
 
 # -------------------------------------------------------------- B200 arm ----
@@ -412,7 +421,7 @@ def run_b200(a):
                      out_pos_cap=G * 160, out_game_cap=2 * G + 64, node_cap=a.node_cap or None,
                      move_launch=None if a.move_launch < 0 else a.move_launch)
     a.lanes = int(eng.cfg.lanes)
-    run = SelfPlayRunner(eng, ev, use_graph=not a.no_graph)
+    run = SelfPlayRunner(eng, ev, use_graph=not a.no_graph, dedup="auto" if a.dedup else False)
     run.warm_start()
 
     def barrier():
@@ -421,16 +430,20 @@ def run_b200(a):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    step_ms_log = []
+
     def timed(fn, steps):
         barrier()
         c0 = eng.counters()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        e0, e1 = marks[0], marks[-1]
         e0.record()
-        for _ in range(steps):
+        for i in range(steps):
             fn()
-        e1.record()
+            marks[i + 1].record()
         barrier()
         ms = e0.elapsed_time(e1)
+        step_ms_log.append([marks[i].elapsed_time(marks[i + 1]) for i in range(steps)])
         c1 = eng.counters()
         if world > 1:
             t = torch.tensor([ms], device=dev)
@@ -459,7 +472,10 @@ def run_b200(a):
 
     clocks = ClockSampler(local)
     clocks.start()
+    rows0 = run.rows_evaluated
     ms, d = timed(plain_step, a.steps)
+    rows_timed = run.rows_evaluated - rows0
+    buckets_timed = dict(run.bucket_iterations) if run.dedup else None
     clk = clocks.stop()
     eng.raise_on_error()
     sims_total = total(d["sims"])
@@ -534,7 +550,14 @@ def run_b200(a):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 search (u64 boards), bf16 network",
             "data": "synthetic: self-play from the initial position, random-init weights (torch.manual_seed(0))",
             "config": workload_config(a.workload, G, sims, iters),
+            "per_step_ms": step_ms_log[0],
             "engine": {"lanes": a.lanes, "cuda_graph": not a.no_graph, "move_launch": int(eng.cfg.move_launch),
+                       "evaluation_dedup": {"enabled": bool(run.dedup), "buckets": getattr(run, "buckets", None),
+                                            "iterations_by_bucket_since_start": buckets_timed,
+                                            "network_rows_per_evaluation_timed": rows_timed / max(evals_total / world, 1),
+                                            "what": "the network runs on the DISTINCT pending positions of a batch (oth_mcts_dedup), bucketed "
+                                                    "batch sizes; every simulation still gets the evaluation of its own leaf. "
+                                                    "aux.without_dedup is the same run with it off"},
                        "arena_mib": eng.buf_bytes[0] + eng.buf_bytes[1] >> 20,
                        "sharding": "games by id, no collective on the search path",
                        "network_twin": {"residual_conv": "one cuDNN graph relu(bias(conv+residual)) per block" if fused_plans
@@ -556,7 +579,8 @@ def run_b200(a):
             "clocks": clk,
             "roofline": roof,
             # the step's dominant cost is the (library) network: its share of the dense bf16 peak sustained by cuBLAS on this pool
-            "network_roofline": network_roofline(kind, evals_total / (ms * 1e-3), world),
+            # FLOPs the network actually executed: rows evaluated (bucket sizes when de-duplicated), not simulations
+            "network_roofline": network_roofline(kind, total(rows_timed) / (ms * 1e-3), world),
             "search_counters_per_step": {k: d[k] / a.steps for k in ("sims", "evals", "terminal_sims", "moves", "games", "nodes", "copied", "levels", "children")},
         }
     if world > 1:
@@ -569,7 +593,7 @@ def run_b200(a):
     return out, dev
 
 
-def aux_selfplay_rate(dev, workload, steps=8, warm=3, dtype=None, tf32=False, iters=None, with_roofline=False):
+def aux_selfplay_rate(dev, workload, steps=8, warm=3, dtype=None, tf32=False, iters=None, with_roofline=False, dedup="auto"):
     """Resident self-play throughput of another BASELINE config on the same GPU (same pipeline as the
     headline: network twin + oth_mcts_step_fused replayed as a CUDA graph; a step = sims/move iterations).
     dtype torch.float32 (+ tf32) runs the float32 twin of the network: the same-precision comparator of the headline."""
@@ -588,7 +612,7 @@ def aux_selfplay_rate(dev, workload, steps=8, warm=3, dtype=None, tf32=False, it
         eng = MctsEngine(G, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=-1, device=dev,
                          out_pos_cap=G * 80 + 4096, out_game_cap=G + 64)
         ev = BatchedPolicy(fold_for_inference(make_net(kind).to(dev), dtype), dev, torch.float32)
-        run = SelfPlayRunner(eng, ev)
+        run = SelfPlayRunner(eng, ev, dedup=dedup)
         run.warm_start()
         for _ in range(warm):
             run.run_iterations(iters)
@@ -606,7 +630,7 @@ def aux_selfplay_rate(dev, workload, steps=8, warm=3, dtype=None, tf32=False, it
         sims_s = (c1["sims"] - c0["sims"]) / (ms * 1e-3)
         out = {"workload": f"{workload}: {desc}", "net": kind, "network_dtype": str(dtype).replace("torch.", "") + ("+tf32" if dtype == torch.float32 and tf32 else ""),
                "sims_per_s": sims_s, "positions_per_s": (c1["moves"] - c0["moves"]) / (ms * 1e-3), "steps": steps, "warmup": warm,
-               "iters_per_step": iters, "ms_per_step": ms / steps, "lanes": int(eng.cfg.lanes),
+               "iters_per_step": iters, "ms_per_step": ms / steps, "lanes": int(eng.cfg.lanes), "evaluation_dedup": bool(run.dedup),
                "network_roofline": network_roofline(kind, (c1["evals"] - c0["evals"]) / (ms * 1e-3)) if dtype == torch.bfloat16 else None}
         if with_roofline:
             out["roofline"] = measure_kernel_roofline(eng, run, ev, min(iters, 200), workload, per_iteration_ms=ms / steps / iters)
@@ -838,6 +862,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--node-cap", type=int, default=0, help="experiment: arena size per slot (default 48*sims+1024)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--dedup", type=int, default=1, help="evaluation de-duplication (oth_mcts_dedup): 1 on (default), 0 off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
     a = ap.parse_args()
@@ -887,14 +912,19 @@ def main():
             out["aux"]["env_step_api"] = aux_env_step_api(dev)
             other = "c3" if a.workload != "c3" else "c4"  # north_star: both architectures, every BASELINE config
             out["aux"]["other_architecture"] = aux_selfplay_rate(dev, other, with_roofline=True)
+            out["aux"]["other_architecture_without_dedup"] = aux_selfplay_rate(dev, other, dedup=False)
             if a.workload != "c2":
                 out["aux"]["c2_one_game"] = aux_selfplay_rate(dev, "c2", steps=12, warm=3, with_roofline=True)
             out["aux"]["c2_one_self_play_dropin"] = aux_one_self_play(dev)
             # same-precision comparator of the headline: the float32 twin of the same network (TF32 tensor cores, and plain FP32)
             out["aux"]["network_precision"] = {
-                "tf32": aux_selfplay_rate(dev, a.workload, steps=2, warm=1, dtype=torch.float32, tf32=True, iters=40),
-                "fp32": aux_selfplay_rate(dev, a.workload, steps=1, warm=1, dtype=torch.float32, tf32=False, iters=10)}
+                "tf32": aux_selfplay_rate(dev, a.workload, steps=2, warm=1, dtype=torch.float32, tf32=True, iters=40, dedup=False),
+                "fp32": aux_selfplay_rate(dev, a.workload, steps=1, warm=1, dtype=torch.float32, tf32=False, iters=10, dedup=False),
+                "note": "float32 twins of the same network, every leaf evaluated in its own row (compare with aux.without_dedup); "
+                        "fp32 = cuDNN/cuBLAS without tensor cores"}
             out["aux"]["public_api_whole_games"] = aux_public_api(dev, "c3")
+            if out["engine"]["evaluation_dedup"]["enabled"]:  # the same plies with every leaf evaluated in its own row
+                out["aux"]["without_dedup"] = aux_selfplay_rate(dev, a.workload, steps=a.steps, warm=a.warmup, dedup=False)
             import oracle
             oracle.build()
             rate, games = cpu_env_rate(cores)

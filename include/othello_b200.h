@@ -297,6 +297,24 @@ int oth_mcts_step_fused(const oth_mcts_config* cfg, const oth_mcts_buffers* b, c
                         const void* value_preact, int64_t value_stride, int32_t is_bf16, float* priors_out, float* values_out,
                         float* nn_input, void* stream);
 
+/* Evaluation de-duplication.  Concurrent games that start from the same position ask, for their first plies, for
+ * the same leaf positions over and over (the reference evaluates each of them: one Inference.inference call per
+ * simulation per game, MCTS_model.py:325-336 / Models.py:11-31).  oth_mcts_dedup finds the DISTINCT positions among
+ * the slots in OTH_PH_WAIT_EVAL, writes their canonical planes to compact_input [bucket][64] (row u = the u-th
+ * distinct position) and eval_map[slot] = the row that holds the slot's position, or -1 if the slot is not waiting or
+ * its position did not fit into `bucket` rows.  The caller runs the network on the `bucket` rows and hands the
+ * outputs to oth_mcts_step_fused_mapped, which reads logits[eval_map[slot]]; slots mapped to -1 stay as they are and
+ * are served by a later launch.  A slot's sequence of evaluated positions is unchanged, so results depend on this
+ * only through the network's outputs.  stats (device int32[2]) receives {distinct pending positions, waiting slots}
+ * of this batch; bucket = 0 only counts (compact_input / eval_map may be NULL).  workspace: device scratch of
+ * oth_mcts_dedup_workspace_bytes(n_slots) bytes, zero-filled once by the caller. */
+int oth_mcts_dedup_workspace_bytes(int32_t n_slots, int64_t* bytes);
+int oth_mcts_dedup(const oth_mcts_config* cfg, const oth_mcts_buffers* b, int32_t bucket, void* workspace, int64_t workspace_bytes,
+                   float* compact_input, int32_t* eval_map, int32_t* stats, void* stream);
+int oth_mcts_step_fused_mapped(const oth_mcts_config* cfg, const oth_mcts_buffers* b, const void* logits, int64_t logits_stride,
+                               const void* value_preact, int64_t value_stride, int32_t is_bf16, const int32_t* eval_map,
+                               float* priors_out, float* values_out, float* nn_input, void* stream);
+
 /* Refresh OTH_BUF_COUNTERS: sums the per-slot event counters and derives the gauges (WAITING /
  * ACTIVE / ERRORS / MAX_TOP) from the control blocks.  Kept out of the hot kernel; hosts call
  * it when they want totals or need to know whether to stop. */

@@ -36,6 +36,8 @@ def record_self_play(runner, tape, table=None, poll_every=32, max_iterations=200
         snap["planes"] = e.nn_input.view(n, 64).cpu().numpy()
 
     def after():   # what the step kernel consumed for them
+        if runner.last_map is not None:  # de-duplicated batch: slots whose position missed the bucket were not served
+            snap["waiting"] = snap["waiting"] & (runner.last_map.cpu().numpy() >= 0)
         pr, va = e.priors.cpu().numpy(), e.values.cpu().numpy()
         tape.put_planes(snap["planes"], snap["waiting"], pr, va)
         if table is not None:

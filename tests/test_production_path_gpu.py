@@ -24,7 +24,7 @@ TRAIN_ARGS = {"c_puct": 2.0, "dirichlet_alpha": 1.0, "dirichlet_epsilon": 0.3, "
               "num_exploratory_moves": 35, "lambda": 0.98}  # train.py:399-423
 
 
-def _runner(kind, n_slots, sims, lanes, graph, seed, hot_path=0, move_launch=None, dtype="bf16"):
+def _runner(kind, n_slots, sims, lanes, graph, seed, hot_path=0, move_launch=None, dtype="bf16", dedup=False):
     import torch
     from alphazero_othello_b200 import _lib
     from alphazero_othello_b200.Models import AlphaZeroNet, FastOthelloNet, fold_for_inference
@@ -35,7 +35,7 @@ def _runner(kind, n_slots, sims, lanes, graph, seed, hot_path=0, move_launch=Non
     e = MctsEngine(n_slots, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=1, seed=seed, lanes=lanes,
                    hot_path=hot_path, move_launch=move_launch)
     ev = BatchedPolicy(fold_for_inference(net, torch.bfloat16 if dtype == "bf16" else torch.float32), "cuda:0", torch.float32)
-    run = SelfPlayRunner(e, ev, use_graph=graph, record=True)
+    run = SelfPlayRunner(e, ev, use_graph=graph, record=True, dedup=dedup)
     assert run.fused, "the production path is the fused one"
     return e, run, args
 
@@ -77,6 +77,64 @@ def test_fused_step_and_move_kernels_with_the_real_network_replay_through_the_or
         print(f"\n[row invariance] {kind} net, {n_slots} slots: {inserted} distinct positions, {repeated} identical repeats, "
               f"{conflicts} repeats with a different output")
         assert inserted + repeated + conflicts == c["evals"] and repeated + conflicts > 0  # the games share their openings
+
+
+@pytest.mark.parametrize("graph,force_bucket", [(True, None), (False, None), (True, 256)])
+def test_evaluation_dedup_replays_through_the_oracle(graph, force_bucket):
+    """oth_mcts_dedup + oth_mcts_step_fused_mapped: the network runs on the distinct pending positions of a batch (bucketed
+    batch sizes, one CUDA graph each), every slot reads its outputs through eval_map.  512 whole games: each game's tape of
+    consumed evaluations replays bit-exactly through the oracle -- also with the bucket forced to 256 rows all game long,
+    when half of the waiting slots miss every launch and are served later."""
+    import oracle as O
+    from oracle.record_replay import record_self_play, replay_and_compare
+    n_slots, sims = 512, 48
+    e, run, args = _runner("small", n_slots, sims, 8, graph, seed=77, dedup=True)
+    assert run.dedup and run.buckets == [256]
+    run.force_bucket = force_bucket
+    tape = O.EvalTape(n_slots, sims * 70 + 128)
+    record_self_play(run, tape, poll_every=64)
+    e.raise_on_error()
+    c = e.counters()
+    assert c["games"] == n_slots and c["errors"] == 0 and c["sims"] == sims * c["moves"]
+    used = run.bucket_iterations
+    assert used[256] > sims * 3, used            # the opening was played on compacted batches ...
+    assert force_bucket or used[0] > sims * 20   # ... the middle game on whole batches
+    assert run.rows_evaluated < (used[0] + used[256]) * n_slots
+    checked, oracle_sims = replay_and_compare(e, args, tape)
+    assert checked == n_slots and oracle_sims == c["sims"] and tape.served == c["evals"]
+
+
+def test_dedup_kernel_maps_identical_positions_to_one_row():
+    """oth_mcts_dedup on a fresh engine: every slot waits for the initial position -> one distinct row, eval_map all 0,
+    the row's planes are the canonical start position; bucket 0 only counts."""
+    import torch
+    from alphazero_othello_b200 import _lib
+    from alphazero_othello_b200.engine import MctsEngine
+    import ctypes as C
+    n = 1000
+    e = MctsEngine(n, dict(TRAIN_ARGS, num_simulations=8), self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=1, lanes=8)
+    e.reset()
+    e.priors.fill_(1.0 / 65); e.values.zero_()
+    e.step()
+    nb = C.c_int64(0)
+    _lib.check(e.L.oth_mcts_dedup_workspace_bytes(n, C.byref(nb)))
+    ws = torch.zeros(nb.value, dtype=torch.uint8, device="cuda")
+    x = torch.full((256, 1, 8, 8), 7.0, device="cuda")
+    emap = torch.full((n,), -5, dtype=torch.int32, device="cuda")
+    stats = torch.zeros(2, dtype=torch.int32, device="cuda")
+    e.dedup(0, None, None, stats, ws)
+    assert stats.tolist() == [1, n]
+    e.dedup(256, x, emap, stats, ws)
+    assert stats.tolist() == [1, n] and (emap == 0).all()
+    assert torch.equal(x[0], e.nn_input[0]) and (x[1:] == 0).all()
+    # a few iterations later the slots have diverged (different root noise): several distinct rows, every waiting slot mapped
+    for _ in range(6):
+        e.step()
+    e.dedup(256, x, emap, stats, ws)
+    u, w = stats.tolist()
+    assert 1 < u <= 256 and w == n and int(emap.max()) == u - 1 and int(emap.min()) == 0
+    planes = e.nn_input.view(n, 64)
+    assert torch.equal(x.view(256, 64)[emap.long()], planes)  # each slot's row holds exactly its own position
 
 
 def _stub_engine(n, sims, lanes, split, seed, salt, move_launch=None, hot_path=0, **kw):

@@ -14,13 +14,14 @@ from bench import TRAIN_ARGS, WORKLOADS, make_net
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "c3"
 gps = int(sys.argv[2]) if len(sys.argv) > 2 else 1  # games per slot: > 1 shows the desynchronised steady state
+dedup = (sys.argv[3] != "0") if len(sys.argv) > 3 else "auto"  # evaluation de-duplication: auto (default) / 1 / 0
 desc, kind, G, sims = WORKLOADS[wl]
 args = dict(TRAIN_ARGS, num_simulations=sims)
 dev = torch.device("cuda:0")
 net = fold_for_inference(make_net(kind).to(dev), torch.bfloat16)
 eng = MctsEngine(G, args, self_play=True, eval_kind=_lib.EVAL_EXTERNAL, games_per_slot=gps, device=dev, seed=1,
                  out_pos_cap=G * gps * 72, out_game_cap=G * gps + 16)
-run = SelfPlayRunner(eng, BatchedPolicy(net, dev, torch.float32))
+run = SelfPlayRunner(eng, BatchedPolicy(net, dev, torch.float32), dedup=dedup)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 run.warm_start()
@@ -42,7 +43,9 @@ torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 out = eng.drain()
 c = eng.counters()
-print(json.dumps({"workload": f"{wl}: {desc}", "complete_games": int(out["games"].shape[0]), "positions": int(out["values"].numel()),
+print(json.dumps({"workload": f"{wl}: {desc}", "evaluation_dedup": bool(run.dedup),
+                  "iterations_by_bucket": getattr(run, "bucket_iterations", None), "network_rows_evaluated": run.rows_evaluated,
+                  "complete_games": int(out["games"].shape[0]), "positions": int(out["values"].numel()),
                   "seconds": dt, "iterations": it, "sims": c["sims"], "sims_per_s": c["sims"] / dt, "positions_per_s": out["values"].numel() / dt,
                   "terminal_sim_fraction": c["terminal_sims"] / c["sims"], "mean_plies": out["values"].numel() / out["games"].shape[0],
                   "arena_high_water": max_top, "node_cap": eng.cfg.node_cap, "max_depth": c["max_depth"],
