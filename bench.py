@@ -195,6 +195,21 @@ def reference_rate(workload, steps, warm, cores):
     return total_sims / total_s, 1e3 * total_s / len(timed), sample
 
 
+def whole_game_profile(workload):
+    """Whole-game throughput with / without evaluation de-duplication: NOT measured in this run (a complete C4 batch takes
+    a minute each way) -- read from the committed runs of tools/full_games.py."""
+    out = {}
+    for dd in (1, 0):
+        p = os.path.join(ROOT, "profiles", f"r02_full_games_{workload}_dedup{dd}.json")
+        if os.path.exists(p):
+            d = json.load(open(p))
+            out["dedup_on" if dd else "dedup_off"] = {"complete_games": d["complete_games"], "seconds": d["seconds"], "sims_per_s": d["sims_per_s"],
+                                                      "positions_per_s": d["positions_per_s"]}
+    if out:
+        out["source"] = f"committed runs profiles/r02_full_games_{workload}_dedup{{1,0}}.json (tools/full_games.py; not measured in this run)"
+    return out or None
+
+
 def workload_config(workload, G, sims, iters):
     """What is computed -- identical in the B200 arm and in the reference arm (the driver compares the two)."""
     node_cap = max(2048, 48 * sims + 1024)
@@ -556,8 +571,10 @@ def run_b200(a):
                                             "iterations_by_bucket_since_start": buckets_timed,
                                             "network_rows_per_evaluation_timed": rows_timed / max(evals_total / world, 1),
                                             "what": "the network runs on the DISTINCT pending positions of a batch (oth_mcts_dedup), bucketed "
-                                                    "batch sizes; every simulation still gets the evaluation of its own leaf. "
-                                                    "aux.without_dedup is the same run with it off"},
+                                                    "batch sizes; every simulation still gets the evaluation of its own leaf. Games start "
+                                                    "together, so the saving sits in the first plies (per_step_ms); aux.without_dedup is the "
+                                                    "same window with it off",
+                                            "whole_games": whole_game_profile(a.workload)},
                        "arena_mib": eng.buf_bytes[0] + eng.buf_bytes[1] >> 20,
                        "sharding": "games by id, no collective on the search path",
                        "network_twin": {"residual_conv": "one cuDNN graph relu(bias(conv+residual)) per block" if fused_plans
@@ -850,8 +867,10 @@ def aux_search_only(dev, G, sims):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
-    ap.add_argument("--warmup", type=int, default=3)
+    # defaults = the window the round-1 driver used: plies 5..24 of games that start together.  (A shorter window close to the
+    # start would sit in the plies where almost every leaf of a batch is a duplicate -- see per_step_ms / aux.without_dedup.)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--games", type=int, default=0, help="override concurrent games per GPU")

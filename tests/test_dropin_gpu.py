@@ -167,3 +167,73 @@ def test_residual_conv_as_one_cudnn_graph_matches_the_two_kernel_path():
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(cap, one)
+
+
+class _RawRows:
+    """What RandomSymmetryDataset (train.py:26-42) becomes: raw rows, no CUDA in __getitem__."""
+
+    def __init__(self, states, pis, vs):
+        self.s, self.p, self.v = states, pis, vs
+
+    def __len__(self):
+        return len(self.s)
+
+    def __getitem__(self, i):
+        import torch
+        return torch.from_numpy(self.s[i]), torch.from_numpy(self.p[i]), torch.tensor(self.v[i], dtype=torch.float32)
+
+
+class _SwappedRows(_RawRows):
+    """The swap INTEGRATION.md warns against: the GPU get_random_symmetry inside a worker."""
+
+    def __getitem__(self, i):
+        from alphazero_othello_b200.envs.othello import get_random_symmetry
+        return get_random_symmetry(self.s[i], self.p[i])
+
+
+def test_augment_batch_with_dataloader_workers():
+    """Training-time symmetry augmentation with DataLoader(num_workers > 0): workers yield raw rows, the
+    training process augments the collated batch on the GPU; every output row is one of the 8 dihedral images of its
+    input row (checked against the oracle's get_symmetries).  Calling the GPU get_random_symmetry from a worker fails
+    with a message that names the replacement instead of a CUDA initialisation error."""
+    import torch
+    import oracle as O
+    from torch.utils.data import DataLoader
+    from alphazero_othello_b200.replay import augment_batch
+    rs = np.random.RandomState(3)
+    n = 64
+    states = rs.randint(-1, 2, size=(n, 8, 8)).astype(np.int8)
+    pis = rs.dirichlet([0.5] * 65, size=n).astype(np.float32)
+    vs = rs.uniform(-1, 1, n).astype(np.float32)
+    seen = 0
+    for s, p, v in DataLoader(_RawRows(states, pis, vs), batch_size=16, shuffle=False, num_workers=2):
+        s2, p2 = augment_batch(s, p, "cuda:0")
+        assert s2.shape == (16, 1, 8, 8) and s2.dtype == torch.float32 and p2.shape == (16, 65)
+        s2, p2 = s2.cpu().numpy(), p2.cpu().numpy()
+        for j in range(16):
+            imgs_s, imgs_p = O.symmetries(states[seen + j], pis[seen + j])
+            assert any(np.array_equal(s2[j, 0], imgs_s[k]) and np.array_equal(p2[j], imgs_p[k]) for k in range(8))
+        seen += 16
+    assert seen == n
+    with pytest.raises(RuntimeError, match="augment_batch"):
+        next(iter(DataLoader(_SwappedRows(states, pis, vs), batch_size=4, num_workers=1)))
+
+
+def test_callers_module_is_left_alone():
+    """collect_self_play_games / MCTS work on a private copy: the trainer's module stays on its device, in its mode."""
+    import torch
+    from alphazero_othello_b200.MCTS_model import MCTS
+    from alphazero_othello_b200.Models import FastOthelloNet
+    from alphazero_othello_b200.envs.othello import OthelloGameNew
+    from alphazero_othello_b200.self_play_worker import collect_self_play_games
+    torch.manual_seed(1)
+    net = FastOthelloNet(8, 65).train()
+    args = {"c_puct": 2.0, "num_simulations": 4, "dirichlet_alpha": 1.0, "dirichlet_epsilon": 0.3, "mcts_temperature": 1.0,
+            "num_exploratory_moves": 5, "lambda": 0.98}
+    games = collect_self_play_games(net, args, 8, n_slots=8)
+    assert len(games) == 8
+    env = OthelloGameNew(8)
+    m = MCTS(env, dict(args, num_threads=4), net)  # num_threads is accepted; the search is sequential (docstring)
+    probs = m.policy_improve_step(env.get_initial_state(), 1, temp=1.0)
+    assert abs(probs.sum() - 1) < 1e-5 and m.root.visit_count == 5
+    assert net.training and next(net.parameters()).device.type == "cpu"

@@ -181,9 +181,9 @@ def _compare_all(e, args, salt, games=None):
 @pytest.mark.parametrize("lanes,move_launch,hot_path", [(8, 1, 0), (16, 0, 0), (32, 1, 0), (8, 1, 2), (32, 0, 5)])
 def test_split_kernel_pair_with_device_stub_400_sims_vs_oracle(lanes, move_launch, hot_path):
     """The production split (64/72-register step kernel + move kernel) with the hash stub where the network would be:
-    400 simulations per move, 64 whole games, every tuple against the oracle; with hot_path = 2 / 5 every deeper path
+    400 simulations per move, 32 whole games, every tuple against the oracle; with hot_path = 2 / 5 every deeper path
     entry goes through OTH_BUF_PATH."""
-    n, sims, salt = 64, 400, 17
+    n, sims, salt = 32, 400, 17
     e, args = _stub_engine(n, sims, lanes, True, seed=5 + lanes, salt=salt, move_launch=move_launch, hot_path=hot_path)
     launches = _run_to_done(e)
     c = e.counters()
