@@ -94,7 +94,10 @@ def test_folded_network_twin(kind):
         l16, v16 = f16(x)
     assert (l32 - lr).abs().max() < 2e-3 and (v32 - vr).abs().max() < 2e-3
     pr, p16 = torch.softmax(lr, -1), torch.softmax(l16, -1)
-    assert (p16 - pr).abs().max() < 0.05 and (v16 - vr).abs().max() < 0.08
+    # measured on a B200 (tools/r2_run8.sh, 4096 positions): bf16 twin |dp| max 1.0e-4 / 6.3e-5, |dv| max 1.4e-3 / 9.6e-4
+    # (small / big net), arg-max agreement 0.99 / 0.98; TF32 twin |dp| 6e-6, |dv| 1e-4.  Bounds = 20x / 7x that.
+    assert (p16 - pr).abs().max() < 2e-3 and (v16 - vr).abs().max() < 1e-2
+    assert (p16.argmax(-1) == pr.argmax(-1)).float().mean() > 0.9
     with torch.no_grad():
         net.val_fc2.bias.add_(0.5) if kind == "big" else net.fc_value2.bias.add_(0.5)
         v_new = refold_(f16, net)(x)[1]
