@@ -496,6 +496,7 @@ def run_b200(a):
     sims_total = total(d["sims"])
     moves_total = total(d["moves"])
     evals_total = total(d["evals"])
+    rows_total = total(rows_timed)  # (collective: every rank)
     value = sims_total / (ms * 1e-3)
     eng.drain(to_host=False)
 
@@ -597,7 +598,7 @@ def run_b200(a):
             "roofline": roof,
             # the step's dominant cost is the (library) network: its share of the dense bf16 peak sustained by cuBLAS on this pool
             # FLOPs the network actually executed: rows evaluated (bucket sizes when de-duplicated), not simulations
-            "network_roofline": network_roofline(kind, total(rows_timed) / (ms * 1e-3), world),
+            "network_roofline": network_roofline(kind, rows_total / (ms * 1e-3), world),
             "search_counters_per_step": {k: d[k] / a.steps for k in ("sims", "evals", "terminal_sims", "moves", "games", "nodes", "copied", "levels", "children")},
         }
     if world > 1:
