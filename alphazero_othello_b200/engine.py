@@ -303,10 +303,10 @@ class SelfPlayRunner:
 
     ``dedup``: evaluation de-duplication (oth_mcts_dedup).  Games that start from the same position ask for the same
     leaves during their first plies; with it the network runs on the DISTINCT pending positions of a batch, padded to
-    the next of a few bucket sizes (n/2, n/4, ... each captured as its own CUDA graph), and the step kernel reads every
+    a few bucket sizes (n/8 ... 7n/8, n/16, n/32; each captured as its own CUDA graph), and the step kernel reads every
     slot's outputs through an index map.  The bucket is chosen on the host from the distinct-position count the device
-    reported a few iterations earlier; positions that do not fit a too-small bucket just wait one launch, so the choice
-    only affects speed.  "auto" enables it for the fused pipeline from 8192 slots up (measured: at 4096 slots of the
+    reported a few iterations earlier; positions that do not fit the bucket just wait one launch, so the choice only
+    affects speed.  "auto" enables it for the fused pipeline from 8192 slots up (measured: at 4096 slots of the
     small network a half-size batch costs 2/3 of a full one and the compaction pass eats the rest)."""
 
     DEDUP_BLOCK = 16  # iterations per host decision (and per throttling event)
@@ -335,11 +335,12 @@ class SelfPlayRunner:
         self.force_bucket = None    # test knob: always use this bucket, however many distinct positions there are
         if self.dedup:
             n, dev = engine.n_slots, engine.device
-            self.buckets = []
-            b = n // 2
-            while b >= max(256, n // 32):
-                self.buckets.append(b)
-                b //= 2
+            # batch sizes the network is captured at: n/8 ... 7n/8 in steps of n/8, then n/16, n/32 (never below 256 rows)
+            self.buckets = sorted({n * k // 8 for k in range(1, 8)} | {n // 16, n // 32}, reverse=True)
+            self.buckets = [b for b in self.buckets if b >= 256 and b % 8 == 0]
+            # launch ramps, the compaction pass and the step kernel, in units of one network row (C4: a 512-row iteration
+            # takes 340 us, a 16 384-row one 2 870 us = 175 ns per row -> ~1 400 rows)
+            self.fixed_cost_rows = max(256, n // 10)
             nb = C.c_int64(0)
             _lib.check(engine.L.oth_mcts_dedup_workspace_bytes(n, C.byref(nb)), "oth_mcts_dedup_workspace_bytes")
             self._ws = torch.zeros(nb.value, dtype=torch.uint8, device=dev)
@@ -405,13 +406,20 @@ class SelfPlayRunner:
             self.after_iteration()
 
     def _choose_bucket(self):
-        """Smallest bucket that holds the distinct positions seen lately with a quarter to spare (the count grows while
-        the trees of a move diverge); 0 = evaluate the whole batch."""
+        """The batch size with the lowest cost per served evaluation.  A bucket of b rows costs (fixed + b) and serves
+        min(u, b) distinct positions (u = distinct pending positions reported lately; positions beyond b wait one launch
+        and are served next time -- rows are never wasted on duplicates, so a bucket BELOW u runs at full efficiency);
+        the whole batch costs n rows and serves all u.  0 = evaluate the whole batch."""
         if self.force_bucket is not None:
             return self.force_bucket
-        need = max(self._recent) * 5 // 4 + 64
-        fit = [b for b in self.buckets if b >= need]
-        return min(fit) if fit else 0
+        n = self.e.n_slots
+        u = max(1, min(n, max(self._recent)))
+        best, best_cost = 0, n / u
+        for b in self.buckets:
+            cost = (self.fixed_cost_rows + b) / min(u, b)
+            if cost < best_cost:
+                best, best_cost = b, cost
+        return best
 
     def _dedup_graph(self, b):
         """The CUDA graph of one iteration variant: b = None plain, 0 whole batch + count, else compacted to b rows.
