@@ -91,13 +91,15 @@ def test_evaluation_dedup_replays_through_the_oracle(graph, force_bucket):
     e, run, args = _runner("small", n_slots, sims, 8, graph, seed=77, dedup=True)
     assert run.dedup and run.buckets == [448, 384, 320, 256]
     run.force_bucket = force_bucket
+    run.fixed_cost_rows = 16  # (at 512 slots the default fixed-cost estimate of 256 rows would never pick a bucket)
     tape = O.EvalTape(n_slots, sims * 70 + 128)
     record_self_play(run, tape, poll_every=64)
     e.raise_on_error()
     c = e.counters()
     assert c["games"] == n_slots and c["errors"] == 0 and c["sims"] == sims * c["moves"]
     used = run.bucket_iterations
-    assert used[256] > sims * 3, used            # the opening was played on compacted batches ...
+    assert used[256] > sims * 3, used            # the opening was played on compacted batches (smallest bucket) ...
+    assert force_bucket or sum(used[b] for b in (448, 384, 320)) > 0, used  # ... the transition on the partial ones, with overflow
     assert force_bucket or used[0] > sims * 20   # ... the middle game on whole batches
     assert run.rows_evaluated < sum(used.values()) * n_slots
     checked, oracle_sims = replay_and_compare(e, args, tape)
