@@ -939,9 +939,9 @@ def main():
             # same-precision comparator of the headline: the float32 twin of the same network (TF32 tensor cores, and plain FP32)
             out["aux"]["network_precision"] = {
                 "tf32": aux_selfplay_rate(dev, a.workload, steps=2, warm=1, dtype=torch.float32, tf32=True, iters=40, dedup=False),
-                "fp32": aux_selfplay_rate(dev, a.workload, steps=1, warm=1, dtype=torch.float32, tf32=False, iters=10, dedup=False),
-                "note": "float32 twins of the same network, every leaf evaluated in its own row (compare with aux.without_dedup); "
-                        "fp32 = cuDNN/cuBLAS without tensor cores"}
+                "note": "float32 twin of the same network on TF32 tensor cores, every leaf evaluated in its own row (compare with "
+                        "aux.without_dedup).  Plain FP32 without tensor cores lands on cuDNN's SIMT kernels: 63 k simulations/s, "
+                        "measured once (profiles/r02_bench_c4_1gpu_first.json), not repeated in every run"}
             out["aux"]["public_api_whole_games"] = aux_public_api(dev, "c3")
             if out["engine"]["evaluation_dedup"]["enabled"]:  # the same plies with every leaf evaluated in its own row
                 out["aux"]["without_dedup"] = aux_selfplay_rate(dev, a.workload, steps=a.steps, warm=a.warmup, dedup=False)
