@@ -338,9 +338,11 @@ class SelfPlayRunner:
             # batch sizes the network is captured at: n/8 ... 7n/8 in steps of n/8, then n/16, n/32 (never below 256 rows)
             self.buckets = sorted({n * k // 8 for k in range(1, 8)} | {n // 16, n // 32}, reverse=True)
             self.buckets = [b for b in self.buckets if b >= 256 and b % 8 == 0]
-            # launch ramps, the compaction pass and the step kernel, in units of one network row (C4: a 512-row iteration
-            # takes 340 us, a 16 384-row one 2 870 us = 175 ns per row -> ~1 400 rows)
+            # cost model of an iteration at b rows until the graphs have been timed (_calibrate): fixed + b, in units of one
+            # network row (C4: a 512-row iteration takes 340 us, a 16 384-row one 2 870 us = 175 ns per row -> ~1 400 rows)
             self.fixed_cost_rows = max(256, n // 10)
+            self.iteration_ms = {}  # measured duration of one iteration per variant ("plain", 0, bucket sizes)
+            self.use_measured_times = True  # False: keep the (fixed + rows) model even after the graphs have been timed
             nb = C.c_int64(0)
             _lib.check(engine.L.oth_mcts_dedup_workspace_bytes(n, C.byref(nb)), "oth_mcts_dedup_workspace_bytes")
             self._ws = torch.zeros(nb.value, dtype=torch.uint8, device=dev)
@@ -414,12 +416,37 @@ class SelfPlayRunner:
             return self.force_bucket
         n = self.e.n_slots
         u = max(1, min(n, max(self._recent)))
+        t = self.iteration_ms
+        if t and self.use_measured_times:  # whole-batch mode = one counting iteration per block, plain ones for the rest
+            k = self.DEDUP_BLOCK
+            best, best_cost = 0, (t[0] + (k - 1) * t["plain"]) / k / u
+            for b in self.buckets:
+                cost = t[b] / min(u, b)
+                if cost < best_cost:
+                    best, best_cost = b, cost
+            return best
         best, best_cost = 0, n / u
         for b in self.buckets:
             cost = (self.fixed_cost_rows + b) / min(u, b)
             if cost < best_cost:
                 best, best_cost = b, cost
         return best
+
+    def _calibrate(self, reps=3):
+        """Time one iteration of every captured variant (the replays are real iterations like any other)."""
+        dev = self.e.device
+        for key, g in self._graphs.items():
+            b = None if key == "plain" else key
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                self.last_map = self._map if b else None
+                self.rows_evaluated += b or self.e.n_slots
+                self.e.launches += 1
+                self._hooked(g.replay)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            self.iteration_ms[key] = e0.elapsed_time(e1) / reps
 
     def _dedup_graph(self, b):
         """The CUDA graph of one iteration variant: b = None plain, 0 whole batch + count, else compacted to b rows.
@@ -434,9 +461,11 @@ class SelfPlayRunner:
         return g
 
     def _run_dedup(self, n):
-        if self.use_graph and not self._graphs:  # every variant is captured up front, not in the middle of a run
+        if self.use_graph and not self._graphs:  # every variant is captured (and timed) up front, not in the middle of a run
             for b in [None, 0] + self.buckets:
                 self._dedup_graph(b)
+            if self.force_bucket is None:
+                self._calibrate()
         done = 0
         while done < n:
             k = min(self.DEDUP_BLOCK, n - done)

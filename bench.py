@@ -569,6 +569,7 @@ def run_b200(a):
             "per_step_ms": step_ms_log[0],
             "engine": {"lanes": a.lanes, "cuda_graph": not a.no_graph, "move_launch": int(eng.cfg.move_launch),
                        "evaluation_dedup": {"enabled": bool(run.dedup), "buckets": getattr(run, "buckets", None),
+                                            "iteration_ms_by_variant": {str(k): v for k, v in getattr(run, "iteration_ms", {}).items()} or None,
                                             "iterations_by_bucket_since_start": buckets_timed,
                                             "network_rows_per_evaluation_timed": rows_timed / max(evals_total / world, 1),
                                             "what": "the network runs on the DISTINCT pending positions of a batch (oth_mcts_dedup), bucketed "

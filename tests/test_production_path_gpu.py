@@ -91,7 +91,9 @@ def test_evaluation_dedup_replays_through_the_oracle(graph, force_bucket):
     e, run, args = _runner("small", n_slots, sims, 8, graph, seed=77, dedup=True)
     assert run.dedup and run.buckets == [448, 384, 320, 256]
     run.force_bucket = force_bucket
-    run.fixed_cost_rows = 16  # (at 512 slots the default fixed-cost estimate of 256 rows would never pick a bucket)
+    # at 512 slots of the small net a compacted batch is not faster than the whole one, and the measured-time policy knows it:
+    # use the (fixed + rows) cost model with a fixed part small enough that the buckets get exercised
+    run.fixed_cost_rows, run.use_measured_times = 16, False
     tape = O.EvalTape(n_slots, sims * 70 + 128)
     record_self_play(run, tape, poll_every=64)
     e.raise_on_error()
@@ -100,6 +102,7 @@ def test_evaluation_dedup_replays_through_the_oracle(graph, force_bucket):
     used = run.bucket_iterations
     assert used[256] > sims * 3, used            # the opening was played on compacted batches (smallest bucket) ...
     assert force_bucket or sum(used[b] for b in (448, 384, 320)) > 0, used  # ... the transition on the partial ones, with overflow
+    assert not (graph and force_bucket is None) or set(run.iteration_ms) == {"plain", 0, 448, 384, 320, 256}  # graphs were timed
     assert force_bucket or used[0] > sims * 20   # ... the middle game on whole batches
     assert run.rows_evaluated < sum(used.values()) * n_slots
     checked, oracle_sims = replay_and_compare(e, args, tape)
