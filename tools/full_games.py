@@ -45,6 +45,7 @@ out = eng.drain()
 c = eng.counters()
 print(json.dumps({"workload": f"{wl}: {desc}", "evaluation_dedup": bool(run.dedup),
                   "iterations_by_bucket": getattr(run, "bucket_iterations", None), "network_rows_evaluated": run.rows_evaluated,
+                  "iteration_ms_by_variant": {str(k): round(v, 4) for k, v in getattr(run, "iteration_ms", {}).items()} or None,
                   "complete_games": int(out["games"].shape[0]), "positions": int(out["values"].numel()),
                   "seconds": dt, "iterations": it, "sims": c["sims"], "sims_per_s": c["sims"] / dt, "positions_per_s": out["values"].numel() / dt,
                   "terminal_sim_fraction": c["terminal_sims"] / c["sims"], "mean_plies": out["values"].numel() / out["games"].shape[0],
