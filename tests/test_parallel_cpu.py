@@ -109,3 +109,29 @@ def test_models_match_reference_when_available():
         p1, v1 = r.inference(s, -1)
         p2, v2 = m.inference(s, -1)
         assert np.array_equal(p1, p2) and v1 == v2
+
+
+def test_dedup_bucket_policy_host_logic():
+    """SelfPlayRunner._choose_bucket (host side of evaluation de-duplication): cost per served evaluation, from the
+    (fixed + rows) model before the graphs are timed and from measured iteration times afterwards."""
+    from types import SimpleNamespace
+    from alphazero_othello_b200.engine import SelfPlayRunner, default_lanes
+    n = 16384
+    buckets = sorted({n * k // 8 for k in range(1, 8)} | {n // 16, n // 32}, reverse=True)
+    me = SimpleNamespace(force_bucket=None, e=SimpleNamespace(n_slots=n), _recent=[n, n], iteration_ms={}, use_measured_times=True,
+                         DEDUP_BLOCK=16, buckets=buckets, fixed_cost_rows=n // 10)
+    choose = lambda u: (setattr(me, "_recent", [u, u]), SelfPlayRunner._choose_bucket(me))[1]
+    assert choose(n) == 0 and choose(16000) == 0          # no duplicates: the whole batch
+    assert choose(1) == 512 and choose(400) == 512        # opening: the smallest bucket
+    assert choose(5400) in (4096, 6144) and choose(9000) == 8192
+    me._recent = [100, 9000]                              # the larger of the last two counts decides
+    assert SelfPlayRunner._choose_bucket(me) == 8192
+    # measured times: a compacted batch that is not faster than the whole one is never chosen
+    me.iteration_ms = {"plain": 0.130, 0: 0.160, **{b: 0.135 for b in buckets}}
+    assert choose(300) == 0
+    me.iteration_ms = {"plain": 2.87, 0: 2.90, **{b: 0.25 + 2.62 * b / n for b in buckets}}
+    assert choose(300) == 512 and choose(n) == 0 and choose(14800) in (14336, 0)
+    me.force_bucket = 2048
+    assert choose(n) == 2048
+    # lanes: a warp per slot while that is one wave, 8 lanes at the C4 geometry
+    assert default_lanes(1) == 32 and default_lanes(4096) == 32 and default_lanes(8192) == 16 and default_lanes(16384) == 8
