@@ -413,10 +413,11 @@ class SelfPlayRunner:
             self.after_iteration()
 
     def _choose_bucket(self):
-        """The batch size with the lowest cost per served evaluation.  A bucket of b rows costs (fixed + b) and serves
+        """The batch size with the lowest cost per served evaluation.  A bucket of b rows costs T(b) -- the measured
+        duration of that graph (_calibrate), or (fixed + b) rows before the graphs have been timed -- and serves
         min(u, b) distinct positions (u = distinct pending positions reported lately; positions beyond b wait one launch
         and are served next time -- rows are never wasted on duplicates, so a bucket BELOW u runs at full efficiency);
-        the whole batch costs n rows and serves all u.  0 = evaluate the whole batch."""
+        the whole batch costs T(n) and serves all u.  0 = evaluate the whole batch."""
         if self.force_bucket is not None:
             return self.force_bucket
         n = self.e.n_slots
@@ -489,7 +490,7 @@ class SelfPlayRunner:
                 else:
                     self._hooked(self._dedup_graph(b).replay)
                 self.e.launches += 1
-                self.bucket_iterations[bucket] += 1
+                self.bucket_iterations[bucket] = self.bucket_iterations.get(bucket, 0) + 1
             ev = torch.cuda.Event()
             ev.record()
             self._events.append(ev)
