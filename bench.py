@@ -543,7 +543,11 @@ def run_b200(a):
         torch.cuda.synchronize(dev)
         mark("outputs")
 
-    e2e_step()  # warm
+    # the e2e window is the value window: the games are started again and warmed up through the same plies, now with
+    # the host-facing work of every step (weights in, targets and finished games out) inside
+    run.warm_start()
+    for _ in range(a.warmup):
+        e2e_step()
     if world > 1:  # NCCL sets up the gather's send/recv connections on first use (~0.25 s at 2 ranks, >1 s at 8): the first
         pay = torch.zeros((1, 69), dtype=torch.float32, device=dev)  # games end at move 9, so do it before the timed region
         dist.gather(pay, [torch.zeros_like(pay) for _ in range(world)] if rank == 0 else None, 0)
@@ -588,8 +592,10 @@ def run_b200(a):
             "positions_per_s": moves_total / (ms * 1e-3),
             "e2e": {"value": e2e_value, "unit": "sims/s", "h2d_bytes_per_step": io["h2d"] // a.steps,
                     "d2h_bytes_per_step": io["d2h"] // a.steps, "ms_per_step": ms2 / a.steps,
+                    "per_step_ms": step_ms_log[1],
                     "includes": "weights H2D from pinned host (+NCCL broadcast if sharded), BN re-fold, "
-                                "D2H of policy targets/root values and finished games' replay tuples (+gather to rank 0)"},
+                                "D2H of policy targets/root values and finished games' replay tuples (+gather to rank 0); "
+                                "same plies as `value` (games restarted, same warm-up)"},
             # this repo's kernels per iteration: k_mcts_step, k_mcts_move, k_stem_im2col_bf16 and -- only when the
             # residual convolutions do not run as one cuDNN graph -- one k_bias_add_relu_bf16 per residual block
             # (with move_launch = 1 the move kernel is launched from the device only in iterations where a move is due:
