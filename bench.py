@@ -488,9 +488,14 @@ def run_b200(a):
     clocks = ClockSampler(local)
     clocks.start()
     rows0 = run.rows_evaluated
+    b0 = dict(run.bucket_iterations) if run.dedup else {}
     ms, d = timed(plain_step, a.steps)
     rows_timed = run.rows_evaluated - rows0
     buckets_timed = dict(run.bucket_iterations) if run.dedup else None
+    # this repo's de-duplication kernels in the timed region: 4 per compacted iteration (keys, heads, emit, planes), 3 per
+    # counting iteration (one per 16-iteration block in whole-batch mode); the CUB sort / scan between them are library code
+    dedup_launches = sum(4 * (v - b0.get(k, 0)) for k, v in (buckets_timed or {}).items() if k) + \
+        3 * (((buckets_timed or {}).get(0, 0) - b0.get(0, 0)) // 16)
     clk = clocks.stop()
     eng.raise_on_error()
     sims_total = total(d["sims"])
@@ -598,9 +603,7 @@ def run_b200(a):
                                 "same plies as `value` (games restarted, same warm-up)"},
             # this repo's kernels per iteration: k_mcts_step, k_mcts_move, k_stem_im2col_bf16 and -- only when the
             # residual convolutions do not run as one cuDNN graph -- one k_bias_add_relu_bf16 per residual block
-            # (with move_launch = 1 the move kernel is launched from the device only in iterations where a move is due:
-            # counted as one per iteration all the same, an upper bound)
-            "gpu_launches": a.steps * iters * (3 + (0 if fused_plans else (5 if kind == "big" else 1))),
+            "gpu_launches": a.steps * iters * (3 + (0 if fused_plans else (5 if kind == "big" else 1))) + dedup_launches,
             "clocks": clk,
             "roofline": roof,
             # the step's dominant cost is the (library) network: its share of the dense bf16 peak sustained by cuBLAS on this pool
