@@ -1300,7 +1300,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_mcts_step_stub(const Params P)
 // Move kernel: one full warp per flagged slot -- policy target, move sampling, trajectory row,
 // breadth-first re-rooting or game hand-off and restart, then the descent that puts the slot's
 // next leaf into the network batch, so a slot never misses an iteration.
-__global__ void __launch_bounds__(kBlock) k_mcts_move(const Params P)
+__global__ void __launch_bounds__(kBlock, 4) k_mcts_move(const Params P)
 {
     __shared__ Scratch scratch[kBlock / 32];
     cg::thread_block_tile<32> tile = cg::tiled_partition<32>(cg::this_thread_block());
@@ -1330,7 +1330,9 @@ __global__ void __launch_bounds__(kBlock) k_mcts_move(const Params P)
 // slot (no scan, and the launch in which every slot moves is spread evenly).  The last block to finish resets the list.
 // (A device-side tail launch of this kernel from the step kernel was tried and removed: inside a captured CUDA graph the
 // child grid is not ordered before the next graph launch, so its control-block updates raced with the next step kernel.)
-__global__ void __launch_bounds__(kBlock) k_mcts_move_list(const Params P)
+// (4 resident blocks per SM = 128 registers: the launch in which all 16 384 slots re-root is bound by how many BFS copies are
+// in flight -- 394 us at 128 registers, 615 us unconstrained at 162, 471 us at 96, 532 us at 80 with their spills.)
+__global__ void __launch_bounds__(kBlock, 4) k_mcts_move_list(const Params P)
 {
     __shared__ Scratch scratch[kBlock / 32];
     __shared__ int s_n;
@@ -1600,7 +1602,7 @@ int mcts_grid(const oth_mcts_config* cfg)
     return (int)(need < full ? need : full);
 }
 
-// k_mcts_move: one warp per set of kMoveSet slots, at most 4 resident blocks' worth per SM (162 registers)
+// k_mcts_move: one warp per set of kMoveSet slots, 4 resident blocks per SM (128 registers)
 inline int move_grid(const oth_mcts_config* cfg)
 {
     const int warps = (cfg->n_slots + kMoveSet - 1) / kMoveSet;
